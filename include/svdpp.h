@@ -1,0 +1,167 @@
+/* svdpp.h — C ABI of libsvdpp.so: the sm_100a kernels behind the SVD denoising-step hot path.
+ *
+ * The reference (inai17ibar/video-diffusion-pipeline-parallel) has no FFI: its boundary for this
+ * path is the Python call  unet(sample, timestep, encoder_hidden_states, added_time_ids)  at
+ * src/models/svd_unet.py:389-395,400-406,416-422 plus the elementwise step maths at :382 and
+ * :427-439.  Each entry point below replaces the library kernels (cuDNN/cuBLAS/SDPA/ATen) that
+ * those lines reach; the comment on each one names the reference lines it stands in for.
+ *
+ * Conventions
+ *  - every pointer is a CUDA device pointer owned by the caller (a torch tensor); fp16 unless
+ *    stated; the library never allocates, frees or retains memory past stream completion;
+ *  - every call enqueues on `stream` (a cudaStream_t passed as void*), never synchronises, and is
+ *    CUDA-graph capturable;
+ *  - return 0 on success, negative on error; svdpp_last_error() returns a thread-local message;
+ *  - activations are channels-last: a [B*F, H, W, C] tensor is the row-major matrix [M = B*F*H*W, C].
+ */
+#ifndef SVDPP_H_
+#define SVDPP_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVDPP_ABI_VERSION 1
+#define SVDPP_MAX_TAPS 9
+
+typedef void* svdpp_stream;
+
+int svdpp_abi_version(void);
+const char* svdpp_last_error(void);
+/* compute capability and SM count of the current device; <0 if no usable device */
+int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution with fused epilogue (tcgen05 + TMEM + TMA).
+ *   acc[m, n] = sum_k A[m, k] * Wt[n, k]                         (fp16 inputs, fp32 accumulate)
+ *   y[m, n]   = alpha * (acc + bias[n] + rowvec[rv(m), n]) + beta1 * R1[m, n] + beta2 * R2[m, n]
+ *   geglu: Wt rows are interleaved per 160-row tile as [80 value | 80 gate];
+ *          D[m, j] = y_value[m, j] * gelu(y_gate[m, j]),  D has N/2 columns.
+ * A is either a plain matrix (optionally the K-concatenation [A | A2], split at K1), or, in conv
+ * mode, the channels-last activation [cB, cF, cH, cW, cC] read through `ntaps` shifted windows
+ * (tap t contributes K-slice [t*cC, (t+1)*cC); out-of-range pixels/frames read as zero).
+ * Replaces: nn.Linear / Conv2d 3x3 / Conv3d (3,1,1) / 1x1 shortcut / GEGLU inside
+ * UNetSpatioTemporalConditionModel (called at svd_unet.py:389-395).
+ * Requirements: K % 64 == 0, K1 % 64 == 0, N % 160 == 0 (pad Wt), 16-byte aligned rows.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct svdpp_gemm_desc {
+  int32_t M, N, K;
+  const void* A;   int64_t lda;          /* row pitch in elements */
+  const void* A2;  int64_t lda2; int32_t K1;   /* optional second source for k >= K1 */
+  int32_t conv;                           /* 0: matrix A; 1: shifted-window activation */
+  int32_t cB, cF, cH, cW, cC;
+  int32_t ntaps;
+  int8_t  taps[SVDPP_MAX_TAPS][4];        /* (dw, dh, df, 0) per tap */
+  const void* Wt;  int64_t ldw;           /* [N, K], K contiguous */
+  const void* bias;                       /* [N] or NULL */
+  const void* rowvec; int64_t rv_ld;      /* [rows, N] or NULL; row = ((m / rv_hw) / rv_div) % rv_mod */
+  int32_t rv_hw, rv_div, rv_mod;
+  const void* R1;  int64_t ldr1; float beta1;
+  const void* R2;  int64_t ldr2; float beta2;
+  float alpha;
+  int32_t geglu;
+  void* D;         int64_t ldd;
+  int32_t n_store;                        /* store columns n < n_store (after geglu halving) */
+} svdpp_gemm_desc;
+
+/* impl: 0 = tcgen05 kernel (the product), 1 = plain CUDA-core kernel (slow; bring-up cross-check) */
+int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatial self-attention over S = H*W tokens per image, head_dim 64, no mask (tcgen05 FMHA).
+ * q/k/v are column blocks of one [n_img*S, ld] matrix: head h of q at columns q_off + 64*h, etc.
+ * Replaces: attn1 of BasicTransformerBlock (SDPA) inside the UNet.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct svdpp_attn_desc {
+  const void* qkv; int64_t ld;
+  int32_t q_off, k_off, v_off;
+  void* out;       int64_t ldo;           /* [n_img*S, heads*64] */
+  int32_t n_img, S, heads;
+  float scale;                            /* 1/sqrt(64) */
+} svdpp_attn_desc;
+int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_stream stream);
+
+/* Temporal self-attention: for every (batch, pixel, head) a sequence of F <= 32 frames.
+ * Token (b, f, p) is row (b*F + f)*HW + p.  Replaces attn1 of TemporalBasicTransformerBlock. */
+int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off,
+                            void* out, int64_t ldo, int32_t B, int32_t F, int32_t HW, int32_t heads,
+                            float scale, svdpp_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bandwidth kernels.
+ * -------------------------------------------------------------------------------------------*/
+/* GroupNorm(32 groups) [+ SiLU] over channels-last input that may be the channel concatenation
+ * [x1 (C1) | x2 (C2)] (the up-block skip cat); statistics per (image, group), or per
+ * (frames_per_stat consecutive images, group) for the temporal ResBlock's 5-D GroupNorm.
+ * out is [n_img*HW, C1+C2].  workspace >= svdpp_groupnorm_workspace_bytes(). Deterministic.
+ * Replaces: nn.GroupNorm + SiLU in ResnetBlock2D / TemporalResnetBlock / transformer norm / conv_norm_out. */
+size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW);
+int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
+                         const void* beta, void* out, int32_t n_img, int32_t HW, int32_t frames_per_stat,
+                         float eps, int32_t apply_silu, void* workspace, size_t workspace_bytes,
+                         svdpp_stream stream);
+
+/* LayerNorm over C of (x[m, :] + addvec[((m / add_hw) % add_mod), :]) with affine; addvec may be NULL.
+ * Replaces: nn.LayerNorm in (Temporal)BasicTransformerBlock; the add is the frame-position embedding. */
+int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, int32_t add_hw, int32_t add_mod,
+                    const void* gamma, const void* beta, void* out, int64_t ldo, int32_t M, int32_t C,
+                    float eps, svdpp_stream stream);
+
+/* y[r, n] = act_out( sum_k act_in(x[r, k] + x_add[r, k]) * W[n, k] + bias[n] ) for a handful of rows
+ * (embedding MLPs, time_emb_proj, 1-token cross-attention value path). x_add may be NULL (same pitch
+ * as x). act: 0 none, 1 SiLU. */
+int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y,
+                       int64_t ldy, int32_t R, int32_t N, int32_t K, int32_t act_in, int32_t act_out,
+                       svdpp_stream stream);
+
+/* Sinusoidal embedding [cos | sin] (flip_sin_to_cos, shift 0) of n_vals scalars into [n_vals, dim] fp16.
+ * src_kind: 0 = fp32 device array, 1 = fp16 device array, 2 = the integers (i % src_mod). */
+int svdpp_sinusoid_embed(const void* src, int32_t src_kind, int32_t src_mod, int32_t n_vals, int32_t dim,
+                         void* out, svdpp_stream stream);
+
+/* Nearest-neighbour 2x upsample, channels-last (Upsample2D before its conv). */
+int svdpp_upsample2x_nhwc(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                          svdpp_stream stream);
+
+/* Gather shifted windows into a matrix: out[m_out, t*C + c] = x[b, f+df, h*stride+dh, w*stride+dw, c]
+ * (zero outside), columns [ntaps*C, ldo) zero-filled.  Used for stride-2 down-sample convs, conv_in
+ * (C = 8) and image widths the TMA window path does not tile. */
+int svdpp_im2col_nhwc(const void* x, void* out, int64_t ldo, int32_t B, int32_t F, int32_t H, int32_t W,
+                      int32_t C, int32_t Ho, int32_t Wo, int32_t stride, int32_t ntaps,
+                      const int8_t* taps /* [ntaps][4] host */, svdpp_stream stream);
+
+/* Build the UNet's channels-last input [B*F, H, W, C0+C1]:
+ *   out[.., c] = fp16(float(src0[b, f, c, h, w]) / in_div)  for c < C0,  src1[...] for c >= C0.
+ * Element strides (in elements) are given per source so both [B,C,F,H,W] (svd_unet.py:382-388:
+ * scale_model_input, cat, permute) and [B,F,C,H,W] (the UNet operator's `sample`) can be read. */
+int svdpp_pack_unet_input(const void* src0, int64_t s0_b, int64_t s0_f, int64_t s0_c, int32_t C0, float in_div,
+                          const void* src1, int64_t s1_b, int64_t s1_f, int64_t s1_c, int32_t C1, void* out,
+                          int32_t out_bfchw /* 0: channels-last, 1: [B,F,C0+C1,H,W] */,
+                          int32_t B, int32_t F, int32_t H, int32_t W, svdpp_stream stream);
+
+/* Channels-last [B*F, H, W, C] -> [B, F, C, H, W] (the UNet operator's return layout). */
+int svdpp_nhwc_to_bfchw(const void* x, void* out, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                        svdpp_stream stream);
+
+/* Classifier-free-guidance combine + v-prediction Euler update, svd_unet.py:410-411,425-439:
+ *   v      = v_cond == NULL ? v_a : fp16(v_a + fp16(gs[f] * fp16(v_cond - v_a)))        (fp16 ops)
+ *   x0     = v * c_v + x / c_x ;  d = (x - x0) / sigma ;  out = fp16(x + d * dt)          (fp32 ops)
+ * with c_v = -sigma/sqrt(sigma^2+1), c_x = sigma^2+1 computed by the caller in fp32.
+ * latent/out are [B, C, F, H, W]; v_* are channels-last [B, F, H, W, C] if v_nhwc else [B, F, C, H, W]. */
+int svdpp_euler_vpred_step(const void* latent, const void* v_a, const void* v_cond, const void* gs,
+                           int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
+                           int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, svdpp_stream stream);
+
+/* DummyUNet step (reference src/models/dummy_unet.py:37-59), fp32, [B, C, F, H, W]:
+ *   out = x + tanh_scale * conv3d(silu(conv3d(x, w1, b1)), w2, b2) + layernorm_C(x) */
+int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* ln_g, const float* ln_b, float ln_eps, float tanh_scale, float* hidden_ws,
+                          float* out, int32_t B, int32_t C, int32_t Ch, int32_t F, int32_t H, int32_t W,
+                          svdpp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDPP_H_ */

@@ -1,0 +1,627 @@
+// HBM-bound kernels of the SVD step: GroupNorm(+SiLU), LayerNorm, embedding MLPs, layout packers,
+// nearest upsample, im2col gather, CFG + Euler update, and the DummyUNet step.
+// All vectorised to 16-byte accesses where the layout allows, coalesced along the contiguous axis,
+// fp32 statistics, deterministic (no floating-point atomics).
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.h"
+
+namespace svdpp {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm
+constexpr int GN_PIX_PER_CHUNK = 64;
+constexpr int GN_GROUPS = 32;
+constexpr int GN_MAX_PAIRS_PER_THREAD = 6;  // 256 threads * 6 pairs * 2 = 3072 channels max
+
+// partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
+                  float2* __restrict__ partial) {
+  extern __shared__ float2 pair_sums[];  // [C/2]
+  const int C = C1 + C2;
+  const int npairs = C >> 1;
+  const int n = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int p0 = chunk * GN_PIX_PER_CHUNK;
+  const int p1 = min(p0 + GN_PIX_PER_CHUNK, HW);
+  float s[GN_MAX_PAIRS_PER_THREAD], ss[GN_MAX_PAIRS_PER_THREAD];
+  const __half* base[GN_MAX_PAIRS_PER_THREAD];
+  int pitch[GN_MAX_PAIRS_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
+    s[k] = 0.f;
+    ss[k] = 0.f;
+    const int cp = threadIdx.x + k * 256;
+    const int c = 2 * cp;
+    if (cp < npairs) {
+      if (c < C1) {
+        base[k] = x1 + static_cast<long long>(n) * HW * C1 + c;
+        pitch[k] = C1;
+      } else {
+        base[k] = x2 + static_cast<long long>(n) * HW * C2 + (c - C1);
+        pitch[k] = C2;
+      }
+    } else {
+      base[k] = nullptr;
+      pitch[k] = 0;
+    }
+  }
+  for (int p = p0; p < p1; ++p) {
+#pragma unroll
+    for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
+      if (base[k] != nullptr) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(base[k] + static_cast<long long>(p) * pitch[k]));
+        s[k] += f.x + f.y;
+        ss[k] += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
+    const int cp = threadIdx.x + k * 256;
+    if (cp < npairs) pair_sums[cp] = make_float2(s[k], ss[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const int ppg = npairs / GN_GROUPS;  // pairs per group
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < ppg; ++i) {
+      const float2 v = pair_sums[threadIdx.x * ppg + i];
+      a += v.x;
+      b += v.y;
+    }
+    partial[(static_cast<long long>(n) * gridDim.x + chunk) * GN_GROUPS + threadIdx.x] = make_float2(a, b);
+  }
+}
+
+// stats[st][g] = (mean, rstd), st = image / frames_per_stat
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int n_chunks, int frames_per_stat,
+                                   float count, float eps, float2* __restrict__ stats) {
+  const int st = blockIdx.x;
+  const int g = threadIdx.x;
+  if (g >= GN_GROUPS) return;
+  double a = 0.0, b = 0.0;
+  for (int f = 0; f < frames_per_stat; ++f) {
+    const long long n = static_cast<long long>(st) * frames_per_stat + f;
+    for (int c = 0; c < n_chunks; ++c) {
+      const float2 v = partial[(n * n_chunks + c) * GN_GROUPS + g];
+      a += v.x;
+      b += v.y;
+    }
+  }
+  const double mean = a / count;
+  double var = b / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[st * GN_GROUPS + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, const float2* __restrict__ stats,
+                __half* __restrict__ out, long long n_vec, int HW, int frames_per_stat, int silu) {
+  const int C = C1 + C2;
+  const int vpr = C >> 3;  // 8-channel vectors per row
+  const int cpg = C / GN_GROUPS;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n_vec;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / vpr;
+    const int c0 = static_cast<int>(idx - m * vpr) << 3;
+    const int st = static_cast<int>(m / HW) / frames_per_stat;
+    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1 + m * C1 + c0)
+                              : *reinterpret_cast<const uint4*>(x2 + m * C2 + (c0 - C1));
+    float v[8], g[8], b[8];
+    unpack8(u, v);
+    unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c0), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 mr = stats[st * GN_GROUPS + (c0 + j) / cpg];
+      float y = (v[j] - mr.x) * mr.y * g[j] + b[j];
+      v[j] = silu ? silu_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(out + m * C + c0) = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAX_VEC = 5;  // per lane: 5 * 8 * 32 = 1280 channels max
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
+                 int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                 __half* __restrict__ out, long long ldo, int M, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (m >= M) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + m * ldx;
+  const __half* ar = addvec ? addvec + static_cast<long long>((m / add_hw) % add_mod) * C : nullptr;
+  float v[LN_MAX_VEC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + vi * 8), v[k]);
+      if (ar) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(ar + vi * 8), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = __half2float(__float2half_rn(v[k][j] + a[j]));  // fp16 add, as torch
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[k][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / C + eps);
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      float g[8], b[8], y[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), g);
+      unpack8(*reinterpret_cast<const uint4*>(beta + vi * 8), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[k][j] - mean) * rstd * g[j] + b[j];
+      *reinterpret_cast<uint4*>(out + m * ldo + vi * 8) = pack8(y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ small linear
+__global__ void __launch_bounds__(128)
+linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ x_add, long long ldx,
+                    const __half* __restrict__ W, long long ldw,
+                    const __half* __restrict__ bias, __half* __restrict__ y, long long ldy, int R, int N, int K,
+                    int act_in, int act_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + warp;
+  if (n >= N) return;
+  const __half* wr = W + static_cast<long long>(n) * ldw;
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k2 = lane; k2 < (K >> 1); k2 += 32) {
+      const float2 w = __half22float2(*reinterpret_cast<const __half2*>(wr + 2 * k2));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r0 + r < R) {
+          float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + static_cast<long long>(r0 + r) * ldx + 2 * k2));
+          if (x_add != nullptr) {
+            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(x_add + static_cast<long long>(r0 + r) * ldx + 2 * k2));
+            a.x = __half2float(__float2half_rn(a.x + a2.x));  // fp16 add, as torch
+            a.y = __half2float(__float2half_rn(a.y + a2.y));
+          }
+          if (act_in == 1) {
+            a.x = __half2float(__float2half_rn(silu_f(a.x)));
+            a.y = __half2float(__float2half_rn(silu_f(a.y)));
+          }
+          acc[r] += a.x * w.x + a.y * w.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+    if (lane == 0) {
+      const float b = bias ? __half2float(bias[n]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r0 + r < R) {
+          float v = acc[r] + b;
+          if (act_out == 1) v = silu_f(__half2float(__float2half_rn(v)));
+          y[static_cast<long long>(r0 + r) * ldy + n] = __float2half_rn(v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ sinusoid
+__global__ void sinusoid_kernel(const void* __restrict__ src, int src_kind, int src_mod, int n_vals, int dim,
+                                __half* __restrict__ out) {
+  const int half_dim = dim >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_vals * half_dim) return;
+  const int i = idx / half_dim, k = idx % half_dim;
+  float t;
+  if (src_kind == 0)
+    t = static_cast<const float*>(src)[i];
+  else if (src_kind == 1)
+    t = __half2float(static_cast<const __half*>(src)[i]);
+  else
+    t = static_cast<float>(i % src_mod);
+  // diffusers get_timestep_embedding: exp(-ln(10000) * k / half_dim), fp32
+  const float expo = (-9.210340371976184f * static_cast<float>(k)) / static_cast<float>(half_dim);
+  const float arg = t * expf(expo);
+  out[static_cast<long long>(i) * dim + k] = __float2half_rn(cosf(arg));             // flip_sin_to_cos: cos first
+  out[static_cast<long long>(i) * dim + half_dim + k] = __float2half_rn(sinf(arg));
+}
+
+// ------------------------------------------------------------------------------------ upsample / im2col / packers
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long n_vec_out, int H,
+                                  int W, int vpc) {
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n_vec_out;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % vpc);
+    long long pix = idx / vpc;
+    const int wo = static_cast<int>(pix % (2 * W));
+    pix /= (2 * W);
+    const int ho = static_cast<int>(pix % (2 * H));
+    const long long n = pix / (2 * H);
+    out[idx] = x[((n * H + (ho >> 1)) * W + (wo >> 1)) * vpc + v];
+  }
+}
+
+struct Taps {
+  int8_t t[SVDPP_MAX_TAPS][4];
+};
+
+__global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long ldo, int F, int H,
+                              int W, int C, int Ho, int Wo, int stride, int ntaps, Taps taps, long long n_vec) {
+  const int vpr = static_cast<int>(ldo >> 3);
+  const int K = ntaps * C;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n_vec;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / vpr;
+    const int k0 = static_cast<int>(idx - m * vpr) << 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (k0 < K) {
+      const int tap = k0 / C, c = k0 - tap * C;
+      const int wo = static_cast<int>(m % Wo);
+      long long r = m / Wo;
+      const int ho = static_cast<int>(r % Ho);
+      r /= Ho;
+      const int f = static_cast<int>(r % F);
+      const long long b = r / F;
+      const int w = wo * stride + taps.t[tap][0], h = ho * stride + taps.t[tap][1], ff = f + taps.t[tap][2];
+      if (w >= 0 && w < W && h >= 0 && h < H && ff >= 0 && ff < F)
+        val = *reinterpret_cast<const uint4*>(x + ((((b * F + ff) * H + h) * W) + w) * C + c);
+    }
+    *reinterpret_cast<uint4*>(out + m * ldo + k0) = val;
+  }
+}
+
+__global__ void pack_unet_input_kernel(const __half* __restrict__ s0, long long s0b, long long s0f, long long s0c,
+                                       int C0, float in_div, const __half* __restrict__ s1, long long s1b,
+                                       long long s1f, long long s1c, int C1, __half* __restrict__ out,
+                                       int out_bfchw, int B, int F, int HW) {
+  const long long total = static_cast<long long>(B) * F * HW;
+  const int C = C0 + C1;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % HW);
+    const long long bf = idx / HW;
+    const int f = static_cast<int>(bf % F);
+    const long long b = bf / F;
+    __half* o = out_bfchw ? out + bf * C * HW + p : out + idx * C;
+    const long long oc = out_bfchw ? HW : 1;
+    for (int c = 0; c < C0; ++c) {
+      const float v = __half2float(s0[b * s0b + f * s0f + c * s0c + p]);
+      o[c * oc] = __float2half_rn(__fdiv_rn(v, in_div));
+    }
+    for (int c = 0; c < C1; ++c) o[(C0 + c) * oc] = s1[b * s1b + f * s1f + c * s1c + p];
+  }
+}
+
+__global__ void nhwc_to_bfchw_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long total, int C,
+                                     int HW) {
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % HW);
+    const long long bf = idx / HW;
+    for (int c = 0; c < C; ++c) out[(bf * C + c) * HW + p] = x[idx * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------ CFG + Euler
+__global__ void euler_vpred_kernel(const __half* __restrict__ latent, const __half* __restrict__ va,
+                                   const __half* __restrict__ vc, const __half* __restrict__ gs, int v_nhwc,
+                                   float c_v, float c_x, float sigma, float dt, __half* __restrict__ out, int B,
+                                   int C, int F, int HW) {
+  const long long total = static_cast<long long>(B) * F * HW;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % HW);
+    const long long bf = idx / HW;
+    const int f = static_cast<int>(bf % F);
+    const long long b = bf / F;
+    for (int c = 0; c < C; ++c) {
+      const long long vi = v_nhwc ? idx * C + c : (bf * C + c) * HW + p;
+      __half v = va[vi];
+      if (vc != nullptr) {
+        // fp16 arithmetic, one rounding per op, as torch does at svd_unet.py:411
+        const __half d = __hsub(vc[vi], v);
+        const __half e = __hmul(gs[f], d);
+        v = __hadd(v, e);
+      }
+      const long long li = ((b * C + c) * F + f) * HW + p;
+      const float x = __half2float(latent[li]);
+      // svd_unet.py:428-437, every op rounded to fp32 separately (no FMA contraction)
+      const float x0 = __fadd_rn(__fmul_rn(__half2float(v), c_v), __fdiv_rn(x, c_x));
+      const float d = __fdiv_rn(__fsub_rn(x, x0), sigma);
+      out[li] = __float2half_rn(__fadd_rn(x, __fmul_rn(d, dt)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ DummyUNet
+// conv3d 3x3x3 pad 1, fp32, [B, Cin, F, H, W] -> [B, Cout, F, H, W]; thread per (voxel, cout)
+__global__ void dummy_conv3d_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y, int B, int Cin, int Cout,
+                                    int F, int H, int W, int silu) {
+  const long long vox = static_cast<long long>(F) * H * W;
+  const long long total = static_cast<long long>(B) * Cout * vox;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wq = static_cast<int>(idx % W);
+  long long r = idx / W;
+  const int h = static_cast<int>(r % H);
+  r /= H;
+  const int f = static_cast<int>(r % F);
+  r /= F;
+  const int co = static_cast<int>(r % Cout);
+  const long long b = r / Cout;
+  float acc = bias[co];
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xp = x + (b * Cin + ci) * vox;
+    const float* wp = w + (static_cast<long long>(co) * Cin + ci) * 27;
+    for (int kf = 0; kf < 3; ++kf) {
+      const int ff = f + kf - 1;
+      if (ff < 0 || ff >= F) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = wq + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          acc += xp[(static_cast<long long>(ff) * H + hh) * W + ww] * wp[(kf * 3 + kh) * 3 + kw];
+        }
+      }
+    }
+  }
+  y[idx] = silu ? acc / (1.0f + expf(-acc)) : acc;
+}
+
+// out = x + scale * conv_out + LN_C(x); thread per voxel
+__global__ void dummy_combine_kernel(const float* __restrict__ x, const float* conv,
+                                     const float* __restrict__ g, const float* __restrict__ bta, float eps,
+                                     float scale, float* out, int B, int C, long long vox) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * vox) return;
+  const long long b = idx / vox, v = idx % vox;
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) mean += x[(b * C + c) * vox + v];
+  mean /= C;
+  float var = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = x[(b * C + c) * vox + v] - mean;
+    var += d * d;
+  }
+  var /= C;
+  const float rstd = g ? 1.0f / sqrtf(var + eps) : 0.f;
+  for (int c = 0; c < C; ++c) {
+    const long long i = (b * C + c) * vox + v;
+    float o = x[i] + scale * conv[i];
+    if (g) o += (x[i] - mean) * rstd * g[c] + bta[c];
+    out[i] = o;
+  }
+}
+
+static inline unsigned grid_for(long long n, int threads, int max_blocks = 148 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace svdpp
+
+using namespace svdpp;
+
+extern "C" size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW) {
+  const size_t n_chunks = (static_cast<size_t>(HW) + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
+  return (static_cast<size_t>(n_img) * n_chunks * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
+}
+
+extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
+                                    const void* beta, void* out, int32_t n_img, int32_t HW, int32_t frames_per_stat,
+                                    float eps, int32_t apply_silu, void* workspace, size_t workspace_bytes,
+                                    svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (x2 == nullptr) C2 = 0;
+  const int C = C1 + C2;
+  SVDPP_CHECK_ARG(x1 && gamma && beta && out && workspace, "groupnorm: null pointer");
+  SVDPP_CHECK_ARG(C % (2 * GN_GROUPS) == 0 && C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
+  SVDPP_CHECK_ARG(C / 2 <= 256 * GN_MAX_PAIRS_PER_THREAD, "groupnorm: C=%d too large", C);
+  SVDPP_CHECK_ARG(frames_per_stat >= 1 && n_img % frames_per_stat == 0, "groupnorm: frames_per_stat=%d", frames_per_stat);
+  SVDPP_CHECK_ARG(workspace_bytes >= svdpp_groupnorm_workspace_bytes(n_img, HW), "groupnorm: workspace too small");
+  const int n_chunks = (HW + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
+  float2* partial = static_cast<float2*>(workspace);
+  float2* stats = partial + static_cast<size_t>(n_img) * n_chunks * GN_GROUPS;
+  dim3 g1(n_chunks, n_img);
+  gn_partial_kernel<<<g1, 256, (C / 2) * sizeof(float2), stream>>>(static_cast<const __half*>(x1), C1,
+                                                                   static_cast<const __half*>(x2), C2, HW, partial);
+  if (int e = check_launch("gn_partial_kernel")) return e;
+  const int n_stats = n_img / frames_per_stat;
+  const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
+  gn_finalize_kernel<<<n_stats, 32, 0, stream>>>(partial, n_chunks, frames_per_stat, count, eps, stats);
+  if (int e = check_launch("gn_finalize_kernel")) return e;
+  const long long n_vec = static_cast<long long>(n_img) * HW * (C / 8);
+  gn_apply_kernel<<<grid_for(n_vec, 256), 256, 0, stream>>>(static_cast<const __half*>(x1), C1,
+                                                            static_cast<const __half*>(x2), C2,
+                                                            static_cast<const __half*>(gamma),
+                                                            static_cast<const __half*>(beta), stats,
+                                                            static_cast<__half*>(out), n_vec, HW, frames_per_stat,
+                                                            apply_silu);
+  return check_launch("gn_apply_kernel");
+}
+
+extern "C" int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, int32_t add_hw, int32_t add_mod,
+                               const void* gamma, const void* beta, void* out, int64_t ldo, int32_t M, int32_t C,
+                               float eps, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && gamma && beta && out, "layernorm: null pointer");
+  SVDPP_CHECK_ARG(C % 8 == 0 && C <= LN_MAX_VEC * 256, "layernorm: C=%d unsupported", C);
+  SVDPP_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0, "layernorm: pitches must be multiples of 8");
+  if (addvec) SVDPP_CHECK_ARG(add_hw > 0 && add_mod > 0, "layernorm: bad addvec indexing");
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, stream>>>(static_cast<const __half*>(x), ldx,
+                                                    static_cast<const __half*>(addvec), add_hw > 0 ? add_hw : 1,
+                                                    add_mod > 0 ? add_mod : 1, static_cast<const __half*>(gamma),
+                                                    static_cast<const __half*>(beta), static_cast<__half*>(out), ldo,
+                                                    M, C, eps);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y,
+                                  int64_t ldy, int32_t R, int32_t N, int32_t K, int32_t act_in, int32_t act_out,
+                                  svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && W && y, "linear_small: null pointer");
+  SVDPP_CHECK_ARG(K % 2 == 0 && ldx % 2 == 0 && ldw % 2 == 0, "linear_small: K and pitches must be even");
+  SVDPP_CHECK_ARG(R >= 1 && N >= 1, "linear_small: bad shape");
+  linear_small_kernel<<<(N + 3) / 4, 128, 0, stream>>>(static_cast<const __half*>(x),
+                                                       static_cast<const __half*>(x_add), ldx,
+                                                       static_cast<const __half*>(W), ldw,
+                                                       static_cast<const __half*>(bias), static_cast<__half*>(y), ldy,
+                                                       R, N, K, act_in, act_out);
+  return check_launch("linear_small_kernel");
+}
+
+extern "C" int svdpp_sinusoid_embed(const void* src, int32_t src_kind, int32_t src_mod, int32_t n_vals, int32_t dim,
+                                    void* out, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(out && dim % 2 == 0 && n_vals > 0, "sinusoid: bad arguments");
+  SVDPP_CHECK_ARG(src_kind == 2 ? src_mod > 0 : src != nullptr, "sinusoid: bad source");
+  const int total = n_vals * (dim / 2);
+  sinusoid_kernel<<<(total + 127) / 128, 128, 0, stream>>>(src, src_kind, src_mod, n_vals, dim,
+                                                           static_cast<__half*>(out));
+  return check_launch("sinusoid_kernel");
+}
+
+extern "C" int svdpp_upsample2x_nhwc(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                     svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && out && C % 8 == 0, "upsample: bad arguments");
+  const long long n_vec = static_cast<long long>(n_img) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(n_vec, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out),
+                                                              n_vec, H, W, C / 8);
+  return check_launch("upsample2x_kernel");
+}
+
+extern "C" int svdpp_im2col_nhwc(const void* x, void* out, int64_t ldo, int32_t B, int32_t F, int32_t H, int32_t W,
+                                 int32_t C, int32_t Ho, int32_t Wo, int32_t stride, int32_t ntaps, const int8_t* taps,
+                                 svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && out && taps, "im2col: null pointer");
+  SVDPP_CHECK_ARG(C % 8 == 0 && ldo % 8 == 0 && ldo >= static_cast<int64_t>(ntaps) * C, "im2col: bad C/ldo");
+  SVDPP_CHECK_ARG(ntaps >= 1 && ntaps <= SVDPP_MAX_TAPS, "im2col: ntaps=%d", ntaps);
+  Taps t{};
+  for (int i = 0; i < ntaps; ++i)
+    for (int j = 0; j < 4; ++j) t.t[i][j] = taps[i * 4 + j];
+  const long long n_vec = static_cast<long long>(B) * F * Ho * Wo * (ldo / 8);
+  im2col_kernel<<<grid_for(n_vec, 256), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out),
+                                                          ldo, F, H, W, C, Ho, Wo, stride, ntaps, t, n_vec);
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int svdpp_pack_unet_input(const void* src0, int64_t s0_b, int64_t s0_f, int64_t s0_c, int32_t C0,
+                                     float in_div, const void* src1, int64_t s1_b, int64_t s1_f, int64_t s1_c,
+                                     int32_t C1, void* out, int32_t out_bfchw, int32_t B, int32_t F, int32_t H,
+                                     int32_t W, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src1 == nullptr) C1 = 0;
+  SVDPP_CHECK_ARG(src0 && out && C0 > 0, "pack_unet_input: bad arguments");
+  const long long total = static_cast<long long>(B) * F * H * W;
+  pack_unet_input_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      static_cast<const __half*>(src0), s0_b, s0_f, s0_c, C0, in_div, static_cast<const __half*>(src1), s1_b, s1_f,
+      s1_c, C1, static_cast<__half*>(out), out_bfchw, B, F, H * W);
+  return check_launch("pack_unet_input_kernel");
+}
+
+extern "C" int svdpp_nhwc_to_bfchw(const void* x, void* out, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                                   svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && out, "nhwc_to_bfchw: null pointer");
+  const long long total = static_cast<long long>(B) * F * H * W;
+  nhwc_to_bfchw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __half*>(x),
+                                                                 static_cast<__half*>(out), total, C, H * W);
+  return check_launch("nhwc_to_bfchw_kernel");
+}
+
+extern "C" int svdpp_euler_vpred_step(const void* latent, const void* v_a, const void* v_cond, const void* gs,
+                                      int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
+                                      int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(latent && v_a && out, "euler: null pointer");
+  SVDPP_CHECK_ARG(v_cond == nullptr || gs != nullptr, "euler: guidance needs gs");
+  const long long total = static_cast<long long>(B) * F * H * W;
+  euler_vpred_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      static_cast<const __half*>(latent), static_cast<const __half*>(v_a), static_cast<const __half*>(v_cond),
+      static_cast<const __half*>(gs), v_nhwc, c_v, c_x, sigma, dt, static_cast<__half*>(out), B, C, F, H * W);
+  return check_launch("euler_vpred_kernel");
+}
+
+extern "C" int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                     const float* ln_g, const float* ln_b, float ln_eps, float tanh_scale,
+                                     float* hidden_ws, float* out, int32_t B, int32_t C, int32_t Ch, int32_t F,
+                                     int32_t H, int32_t W, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && w1 && b1 && w2 && b2 && hidden_ws && out, "dummy_unet: null pointer");
+  const long long vox = static_cast<long long>(F) * H * W;
+  const long long n1 = static_cast<long long>(B) * Ch * vox;
+  dummy_conv3d_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, stream>>>(x, w1, b1, hidden_ws, B, C, Ch, F, H,
+                                                                                   W, 1);
+  if (int e = check_launch("dummy_conv3d_kernel")) return e;
+  // second conv writes into `out`, then the combine kernel rewrites `out` in place
+  const long long n2 = static_cast<long long>(B) * C * vox;
+  dummy_conv3d_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, stream>>>(hidden_ws, w2, b2, out, B, Ch, C, F,
+                                                                                   H, W, 0);
+  if (int e = check_launch("dummy_conv3d_kernel")) return e;
+  dummy_combine_kernel<<<static_cast<unsigned>((B * vox + 255) / 256), 256, 0, stream>>>(x, out, ln_g, ln_b, ln_eps,
+                                                                                         tanh_scale, out, B, C, vox);
+  return check_launch("dummy_combine_kernel");
+}

@@ -1,0 +1,434 @@
+// Self-attention kernels, head_dim 64, fp16 in / fp32 softmax / fp16 out, no mask.
+//
+// svdpp_attn_spatial_f16 (tcgen05): one CTA per (128-query tile, head, image); 2 CTAs per SM.
+//   warps 0..3  softmax: thread = query row; S row read from TMEM, online softmax in the log2
+//               domain, P written as fp16 into 128B-swizzled smem, O kept in registers
+//   warp 4      TMA producer: Q once, then K_j / V_j blocks of 128 keys through 2-slot rings
+//   warp 5      TMEM allocator + MMA issuer: S = Q K_j^T (N=128) and O_j = P_j V_j (N=64, V read
+//               MN-major straight from its row-major tile) into TMEM
+// svdpp_attn_temporal_f16: sequences of F <= 32 frames per (pixel, head): one warp each, CUDA cores
+//   (0.1 % of the UNet's FLOPs; bandwidth bound).
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace svdpp {
+
+struct AttnParams {
+  int S, n_kv;
+  int q_off, k_off, v_off;
+  float scale_log2;
+  __half* out;
+  long long ldo;
+};
+
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 fp16
+constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128;
+
+__global__ void __launch_bounds__(192, 2)
+attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;      // 2 slots
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;  // 2 slots
+  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;  // 2 swizzle atoms (keys 0..63 | 64..127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_ready = bars + 10;
+  uint64_t* pv_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int row_base = img * p.S;  // first token row of this image in the qkv matrix
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("svdpp: attention smem base not 1024-aligned\n");
+    __trap();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // columns [0,128)
+  const uint32_t tmem_O = tmem_base + 128;  // columns [128,192)
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, q_full, p.q_off + head * 64, row_base + q0);
+      for (int j = 0; j < p.n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1, 11);
+        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        tma_load_2d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], p.k_off + head * 64, row_base + j * 128);
+        mbar_wait(&v_empty[s], ph ^ 1, 12);
+        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_2d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], p.v_off + head * 64, row_base + j * 128);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(128, false);
+      constexpr uint32_t idesc_o = make_idesc_f16(64, true);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&k_full[s], (j >> 1) & 1, 13);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_S, make_smem_desc_sw128(q_addr + k * 32, 1024, 0),
+                   make_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&k_empty[s]);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0, 14);
+      issue_s(0);
+      for (int j = 0; j < p.n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_ready, j & 1, 15);  // P_j in smem, S_j fully consumed
+        mbar_wait(&v_full[s], (j >> 1) & 1, 16);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + s * ATT_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 1024, 0);
+          const uint64_t db = make_smem_desc_sw128(v_addr + kk * 2048, 1024, 8192);
+          umma_f16(tmem_O, da, db, idesc_o, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
+        if (j + 1 < p.n_kv) issue_s(j + 1);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax (warps 0..3)
+    const int r = threadIdx.x;  // query row in tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m_run = -CUDART_INF_F;
+    float l_run = 0.f;
+    for (int j = 0; j < p.n_kv; ++j) {
+      const int kv0 = j * 128;
+      const int valid = p.S - kv0;  // keys [0, valid) of this block are real
+      mbar_wait(s_full, j & 1, 17);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (c * 32 + i >= valid) s = -CUDART_INF_F;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);
+      m_run = m_new;
+      if (j > 0) {
+        // fold in O_{j-1} = P_{j-1} V_{j-1}; this also orders our P write after that MMA's P read
+        mbar_wait(pv_done, (j - 1) & 1, 18);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+        }
+      }
+      l_run *= alpha;
+      // pass 2: probabilities -> fp16 -> swizzled smem
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m_new);
+          float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_new);
+          if (c * 32 + 2 * i >= valid) p0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          lsum += p0 + p1;
+          __half2 h = __floats2half2_rn(p0, p1);
+          packed[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      l_run += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    mbar_wait(pv_done, (p.n_kv - 1) & 1, 19);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    __half* dst = p.out + static_cast<long long>(row_base + q) * p.ldo + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
+      tmem_ld_wait();
+      if (q < p.S) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = (o[c * 32 + 2 * i] + __uint_as_float(v[2 * i])) * inv_l;
+          float b = (o[c * 32 + 2 * i + 1] + __uint_as_float(v[2 * i + 1])) * inv_l;
+          __half2 h = __floats2half2_rn(a, b);
+          packed[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) =
+              make_uint4(packed[4 * qd], packed[4 * qd + 1], packed[4 * qd + 2], packed[4 * qd + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// Bring-up cross-check: one thread per (image, head, query), online softmax on CUDA cores.
+__global__ void attn_spatial_simt_kernel(const __half* qkv, long long ld, AttnParams p, int heads, int n_img) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_img) * heads * p.S;
+  if (idx >= total) return;
+  const int q = static_cast<int>(idx % p.S);
+  const int head = static_cast<int>((idx / p.S) % heads);
+  const int img = static_cast<int>(idx / (static_cast<long long>(p.S) * heads));
+  const long long row0 = static_cast<long long>(img) * p.S;
+  const __half* qp = qkv + (row0 + q) * ld + p.q_off + head * 64;
+  float qf[64], o[64];
+  for (int i = 0; i < 64; ++i) {
+    qf[i] = __half2float(qp[i]);
+    o[i] = 0.f;
+  }
+  float m = -CUDART_INF_F, l = 0.f;
+  for (int k = 0; k < p.S; ++k) {
+    const __half* kp = qkv + (row0 + k) * ld + p.k_off + head * 64;
+    const __half* vp = qkv + (row0 + k) * ld + p.v_off + head * 64;
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += qf[i] * __half2float(kp[i]);
+    s *= p.scale_log2;
+    const float mn = fmaxf(m, s);
+    const float a = exp2f(m - mn);
+    const float pr = exp2f(s - mn);
+    l = l * a + pr;
+    const float prh = __half2float(__float2half_rn(pr));
+    for (int i = 0; i < 64; ++i) o[i] = o[i] * a + prh * __half2float(vp[i]);
+    m = mn;
+  }
+  __half* dst = p.out + (row0 + q) * p.ldo + head * 64;
+  for (int i = 0; i < 64; ++i) dst[i] = __float2half_rn(o[i] / l);
+}
+
+// Temporal attention: warp per (batch, pixel, head); lane = frame.
+__global__ void __launch_bounds__(128)
+attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, int k_off, int v_off,
+                     __half* __restrict__ out, long long ldo, int B, int F, int HW, int heads, float scale_log2) {
+  __shared__ __align__(16) __half sK[4][32][72];  // padded rows (144 B) to spread banks
+  __shared__ __align__(16) __half sV[4][32][72];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long unit = static_cast<long long>(blockIdx.x) * 4 + warp;
+  const long long total = static_cast<long long>(B) * HW * heads;
+  if (unit >= total) return;
+  const int head = static_cast<int>(unit % heads);
+  const long long bp = unit / heads;
+  const int pix = static_cast<int>(bp % HW);
+  const int b = static_cast<int>(bp / HW);
+  const bool active = lane < F;
+  const long long row = (static_cast<long long>(b) * F + (active ? lane : 0)) * HW + pix;
+  const __half* base = qkv + row * ld + head * 64;
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base + q_off);
+    const uint4* kp = reinterpret_cast<const uint4*>(base + k_off);
+    const uint4* vp = reinterpret_cast<const uint4*>(base + v_off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 u = qp[i];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(h[t]);
+        q[i * 8 + 2 * t] = f.x;
+        q[i * 8 + 2 * t + 1] = f.y;
+      }
+      if (active) {
+        *reinterpret_cast<uint4*>(&sK[warp][lane][i * 8]) = kp[i];
+        *reinterpret_cast<uint4*>(&sV[warp][lane][i * 8]) = vp[i];
+      }
+    }
+  }
+  __syncwarp();
+  float s[32];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    s[k] = -CUDART_INF_F;
+    if (k < F) {  // warp-uniform
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float2 kk = __half22float2(*reinterpret_cast<const __half2*>(&sK[warp][k][2 * i]));
+        acc += q[2 * i] * kk.x + q[2 * i + 1] * kk.y;
+      }
+      acc *= scale_log2;
+      s[k] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+  float l = 0.f;
+  float o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < F) {
+      const float pr = exp2f(s[k] - mx);
+      l += pr;
+      const float prh = __half2float(__float2half_rn(pr));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float2 vv = __half22float2(*reinterpret_cast<const __half2*>(&sV[warp][k][2 * i]));
+        o[2 * i] += prh * vv.x;
+        o[2 * i + 1] += prh * vv.y;
+      }
+    }
+  }
+  if (active) {
+    const float inv = 1.0f / l;
+    __half* dst = out + row * ldo + head * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h0 = __floats2half2_rn(o[i * 8 + 0] * inv, o[i * 8 + 1] * inv);
+      __half2 h1 = __floats2half2_rn(o[i * 8 + 2] * inv, o[i * 8 + 3] * inv);
+      __half2 h2 = __floats2half2_rn(o[i * 8 + 4] * inv, o[i * 8 + 5] * inv);
+      __half2 h3 = __floats2half2_rn(o[i * 8 + 6] * inv, o[i * 8 + 7] * inv);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2);
+      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst + i * 8) = u;
+    }
+  }
+}
+
+}  // namespace svdpp
+
+using namespace svdpp;
+
+extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(d && d->qkv && d->out, "attn: null pointers");
+  SVDPP_CHECK_ARG(d->n_img > 0 && d->S > 0 && d->heads > 0, "attn: bad shape");
+  SVDPP_CHECK_ARG(d->ld % 8 == 0 && d->ldo % 8 == 0, "attn: pitches must be multiples of 8");
+  SVDPP_CHECK_ARG(d->q_off % 8 == 0 && d->k_off % 8 == 0 && d->v_off % 8 == 0, "attn: offsets must be multiples of 8");
+  AttnParams p{};
+  p.S = d->S;
+  p.n_kv = (d->S + 127) / 128;
+  p.q_off = d->q_off;
+  p.k_off = d->k_off;
+  p.v_off = d->v_off;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.out = static_cast<__half*>(d->out);
+  p.ldo = d->ldo;
+  if (impl == 1) {
+    const long long total = static_cast<long long>(d->n_img) * d->heads * d->S;
+    attn_spatial_simt_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
+        static_cast<const __half*>(d->qkv), d->ld, p, d->heads, d->n_img);
+    return check_launch("attn_spatial_simt_kernel");
+  }
+  SVDPP_CHECK_ARG(impl == 0, "attn: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(d->heads <= 65535 && d->n_img <= 65535, "attn: grid too large");
+  CUtensorMap tm;
+  const long long rows = static_cast<long long>(d->n_img) * d->S;
+  uint64_t dims[2] = {static_cast<uint64_t>(d->ld), static_cast<uint64_t>(rows)};
+  uint64_t str[1] = {static_cast<uint64_t>(d->ld) * 2};
+  uint32_t box[2] = {64, 128};
+  if (encode_tmap_f16(&tm, d->qkv, 2, dims, str, box)) return -5;
+  static bool configured = false;
+  if (!configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(attn_spatial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((d->S + 127) / 128, d->heads, d->n_img);
+  attn_spatial_tc_kernel<<<grid, 192, ATT_SMEM_BYTES, stream>>>(tm, p);
+  return check_launch("attn_spatial_tc_kernel");
+}
+
+extern "C" int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off,
+                                        void* out, int64_t ldo, int32_t B, int32_t F, int32_t HW, int32_t heads,
+                                        float scale, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(qkv && out, "attn_temporal: null pointers");
+  SVDPP_CHECK_ARG(F >= 1 && F <= 32, "attn_temporal: F=%d must be in [1,32]", F);
+  SVDPP_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+                  "attn_temporal: pitches/offsets must be multiples of 8");
+  const long long units = static_cast<long long>(B) * HW * heads;
+  const unsigned blocks = static_cast<unsigned>((units + 3) / 4);
+  attn_temporal_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off, v_off,
+                                                   static_cast<__half*>(out), ldo, B, F, HW, heads,
+                                                   scale * 1.4426950408889634f);
+  return check_launch("attn_temporal_kernel");
+}

@@ -1,0 +1,534 @@
+// svdpp_gemm_f16: fp16 GEMM / implicit-GEMM convolution with a fused epilogue, sm_100a.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   global -> 128B-swizzled smem ring (A tile 128x64, B tile BNx64)
+//   warp 1      MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
+//   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages)
+//   warps 4..7  epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16 stores
+// The two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Convolutions never materialise im2col: for tap (dw,dh,df) the producer loads the activation
+// window shifted by the tap through a 5-D tensor map [C, W, H, F, B]; TMA zero-fills the halo.
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace svdpp {
+
+struct GemmParams {
+  int M, N;
+  int num_kb, kb_split;
+  int conv, cF, cH, cW, cpk, nrows, bw;
+  int8_t taps[SVDPP_MAX_TAPS][4];
+  const __half* bias;
+  const __half* rowvec;
+  long long rv_ld;
+  int rv_hw, rv_div, rv_mod;
+  const __half* R1;
+  long long ldr1;
+  float beta1;
+  const __half* R2;
+  long long ldr2;
+  float beta2;
+  float alpha;
+  __half* D;
+  long long ldd;
+  int n_store;
+  int m_tiles, n_tiles;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// torch fp16 semantics of GEGLU: proj output rounded to fp16, gelu(gate) rounded, product rounded
+__device__ __forceinline__ __half geglu_fp16(float val, float gate) {
+  __half v16 = __float2half_rn(val);
+  __half g16 = __float2half_rn(gate);
+  __half ge = __float2half_rn(gelu_erf(__half2float(g16)));
+  return __hmul(v16, ge);
+}
+
+__device__ __forceinline__ void load8(const __half* p, float (&o)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+
+template <int BN, bool GEGLU>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 160) ? 5 : 4;
+  static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
+  static constexpr int NOUT = GEGLU ? BN / 2 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool GEGLU>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN, GEGLU>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * Cfg::BM;
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 1);
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (!p.conv) {
+            if (kb < p.kb_split)
+              tma_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
+            else
+              tma_load_2d(sa, &tmA2, &full[stage], (kb - p.kb_split) * 64, m0);
+          } else {
+            const int tap = kb / p.cpk;
+            const int c0 = (kb - tap * p.cpk) * 64;
+            const int dw = p.taps[tap][0], dh = p.taps[tap][1], df = p.taps[tap][2];
+            for (int r = 0; r < p.nrows; ++r) {
+              const int px = m0 + r * p.bw;
+              const int w = px % p.cW;
+              const int row = px / p.cW;
+              const int h = row % p.cH;
+              const int img = row / p.cH;
+              const int f = img % p.cF;
+              const int b = img / p.cF;
+              tma_load_5d(sa + r * p.bw * 128, &tmA, &full[stage], c0, w + dw, h + dh, f + df, b);
+            }
+          }
+          tma_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
+            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int we = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = we * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
+      const int m = m_tile * Cfg::BM + row;
+      const bool m_ok = m < p.M;
+      mbar_wait(&tfull[as], aphase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + as * Cfg::ACC_STRIDE;
+      const __half* rv = nullptr;
+      if (p.rowvec != nullptr && m_ok) {
+        const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
+        rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld;
+      }
+#pragma unroll 1
+      for (int c = 0; c < Cfg::NOUT / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c * 16, v);
+        uint32_t g[16];
+        if constexpr (GEGLU) tmem_ld_x16(taddr + BN / 2 + c * 16, g);
+        tmem_ld_wait();
+        const int nw = n_tile * BN + c * 16;           // weight-row index of the value columns
+        const int nout = n_tile * Cfg::NOUT + c * 16;  // output column
+        if (m_ok && nout < p.n_store) {
+          float y[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            float b8[8];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              load8(p.bias + nw + hlf * 8, b8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+            }
+          }
+          __half o[16];
+          if constexpr (GEGLU) {
+            float gt[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
+            if (p.bias != nullptr) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(p.bias + nw + BN / 2 + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gt[hlf * 8 + j] += b8[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = geglu_fp16(y[j], gt[j]);
+          } else {
+            if (rv != nullptr) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(rv + nw + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] *= p.alpha;
+            if (p.R1 != nullptr) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(p.R1 + static_cast<long long>(m) * p.ldr1 + nout + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
+              }
+            }
+            if (p.R2 != nullptr) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(y[j]);
+          }
+          __half* dst = p.D + static_cast<long long>(m) * p.ldd + nout;
+          if (nout + 16 <= p.n_store && (p.ldd & 7) == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            const uint4* o4 = reinterpret_cast<const uint4*>(o);
+            d4[0] = o4[0];
+            d4[1] = o4[1];
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (nout + j < p.n_store) dst[j] = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Plain CUDA-core kernel with identical semantics (one thread per output). Bring-up cross-check only.
+// ----------------------------------------------------------------------------------------------
+struct SimtParams {
+  int M, N, K, K1;
+  const __half* A;
+  long long lda;
+  const __half* A2;
+  long long lda2;
+  int conv, cB, cF, cH, cW, cC, ntaps;
+  int8_t taps[SVDPP_MAX_TAPS][4];
+  const __half* Wt;
+  long long ldw;
+  GemmParams ep;  // epilogue fields reused
+  int geglu;
+  int bn;
+};
+
+__device__ __forceinline__ float simt_dot(const SimtParams& p, int m, int n) {
+  float acc = 0.f;
+  const __half* wrow = p.Wt + static_cast<long long>(n) * p.ldw;
+  if (!p.conv) {
+    for (int k = 0; k < p.K; ++k) {
+      float a = (p.A2 != nullptr && k >= p.K1)
+                    ? __half2float(p.A2[static_cast<long long>(m) * p.lda2 + (k - p.K1)])
+                    : __half2float(p.A[static_cast<long long>(m) * p.lda + k]);
+      acc += a * __half2float(wrow[k]);
+    }
+  } else {
+    int w = m % p.cW;
+    int r = m / p.cW;
+    int h = r % p.cH;
+    int img = r / p.cH;
+    int f = img % p.cF;
+    int b = img / p.cF;
+    for (int t = 0; t < p.ntaps; ++t) {
+      int ww = w + p.taps[t][0], hh = h + p.taps[t][1], ff = f + p.taps[t][2];
+      if (ww < 0 || ww >= p.cW || hh < 0 || hh >= p.cH || ff < 0 || ff >= p.cF) continue;
+      const __half* src = p.A + ((((static_cast<long long>(b) * p.cF + ff) * p.cH + hh) * p.cW) + ww) * p.cC;
+      const __half* wk = wrow + t * p.cC;
+      for (int c = 0; c < p.cC; ++c) acc += __half2float(src[c]) * __half2float(wk[c]);
+    }
+  }
+  return acc;
+}
+
+__global__ void gemm_simt_kernel(const SimtParams p) {
+  const int nout_total = p.geglu ? p.N / 2 : p.N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(p.M) * nout_total) return;
+  const int m = static_cast<int>(idx / nout_total);
+  const int nout = static_cast<int>(idx % nout_total);
+  if (nout >= p.ep.n_store) return;
+  const GemmParams& e = p.ep;
+  __half o;
+  if (p.geglu) {
+    const int half_bn = p.bn / 2;
+    const int nt = nout / half_bn, j = nout % half_bn;
+    const int nv = nt * p.bn + j, ng = nv + half_bn;
+    float val = simt_dot(p, m, nv), gate = simt_dot(p, m, ng);
+    if (e.bias) {
+      val += __half2float(e.bias[nv]);
+      gate += __half2float(e.bias[ng]);
+    }
+    o = geglu_fp16(val, gate);
+  } else {
+    float y = simt_dot(p, m, nout);
+    if (e.bias) y += __half2float(e.bias[nout]);
+    if (e.rowvec) {
+      const int rr = ((m / e.rv_hw) / e.rv_div) % e.rv_mod;
+      y += __half2float(e.rowvec[static_cast<long long>(rr) * e.rv_ld + nout]);
+    }
+    y *= e.alpha;
+    if (e.R1) y += e.beta1 * __half2float(e.R1[static_cast<long long>(m) * e.ldr1 + nout]);
+    if (e.R2) y += e.beta2 * __half2float(e.R2[static_cast<long long>(m) * e.ldr2 + nout]);
+    o = __float2half_rn(y);
+  }
+  e.D[static_cast<long long>(m) * e.ldd + nout] = o;
+}
+
+template <int BN, bool GEGLU>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                     const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, GEGLU>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, GEGLU>;
+  if (!configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace svdpp
+
+using namespace svdpp;
+
+extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  constexpr int BN = 160;
+  SVDPP_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
+  SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
+  SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
+  SVDPP_CHECK_ARG(d->A && d->Wt && d->D, "gemm: null A/Wt/D");
+  SVDPP_CHECK_ARG(!(d->geglu && (d->rowvec || d->R1 || d->R2)), "gemm: geglu epilogue takes bias only");
+  const int nout_total = d->geglu ? d->N / 2 : d->N;
+  const int n_store = d->n_store > 0 ? (d->n_store < nout_total ? d->n_store : nout_total) : nout_total;
+
+  GemmParams p{};
+  p.M = d->M;
+  p.N = d->N;
+  p.num_kb = d->K / 64;
+  p.kb_split = p.num_kb;
+  p.conv = d->conv;
+  p.bias = static_cast<const __half*>(d->bias);
+  p.rowvec = static_cast<const __half*>(d->rowvec);
+  p.rv_ld = d->rv_ld;
+  p.rv_hw = d->rv_hw > 0 ? d->rv_hw : 1;
+  p.rv_div = d->rv_div > 0 ? d->rv_div : 1;
+  p.rv_mod = d->rv_mod > 0 ? d->rv_mod : 0x7fffffff;
+  p.R1 = static_cast<const __half*>(d->R1);
+  p.ldr1 = d->ldr1;
+  p.beta1 = d->beta1;
+  p.R2 = static_cast<const __half*>(d->R2);
+  p.ldr2 = d->ldr2;
+  p.beta2 = d->beta2;
+  p.alpha = d->alpha;
+  p.D = static_cast<__half*>(d->D);
+  p.ldd = d->ldd;
+  p.n_store = n_store;
+  p.m_tiles = (d->M + 127) / 128;
+  p.n_tiles = d->N / BN;
+
+  if (d->conv) {
+    SVDPP_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SVDPP_MAX_TAPS, "gemm: ntaps=%d", d->ntaps);
+    SVDPP_CHECK_ARG(d->K == d->ntaps * d->cC, "gemm: conv K=%d != ntaps*C=%d", d->K, d->ntaps * d->cC);
+    SVDPP_CHECK_ARG(static_cast<long long>(d->cB) * d->cF * d->cH * d->cW == d->M, "gemm: conv dims do not give M");
+    SVDPP_CHECK_ARG(d->A2 == nullptr, "gemm: conv mode takes one source");
+    for (int t = 0; t < d->ntaps; ++t)
+      for (int j = 0; j < 4; ++j) p.taps[t][j] = d->taps[t][j];
+    p.cF = d->cF;
+    p.cH = d->cH;
+    p.cW = d->cW;
+  }
+
+  if (impl == 1) {
+    SimtParams sp{};
+    sp.M = d->M;
+    sp.N = d->N;
+    sp.K = d->K;
+    sp.K1 = d->A2 ? d->K1 : d->K;
+    sp.A = static_cast<const __half*>(d->A);
+    sp.lda = d->lda;
+    sp.A2 = static_cast<const __half*>(d->A2);
+    sp.lda2 = d->lda2;
+    sp.conv = d->conv;
+    sp.cB = d->cB;
+    sp.cF = d->cF;
+    sp.cH = d->cH;
+    sp.cW = d->cW;
+    sp.cC = d->cC;
+    sp.ntaps = d->ntaps;
+    for (int t = 0; t < SVDPP_MAX_TAPS; ++t)
+      for (int j = 0; j < 4; ++j) sp.taps[t][j] = d->taps[t][j];
+    sp.Wt = static_cast<const __half*>(d->Wt);
+    sp.ldw = d->ldw;
+    sp.ep = p;
+    sp.geglu = d->geglu;
+    sp.bn = BN;
+    const long long total = static_cast<long long>(d->M) * nout_total;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
+    return check_launch("gemm_simt_kernel");
+  }
+  SVDPP_CHECK_ARG(impl == 0, "gemm: unknown impl %d", impl);
+
+  CUtensorMap tmA, tmA2, tmB;
+  if (!d->conv) {
+    const int K1 = d->A2 ? d->K1 : d->K;
+    SVDPP_CHECK_ARG(K1 > 0 && K1 % 64 == 0 && K1 <= d->K, "gemm: K1=%d must be a multiple of 64", K1);
+    SVDPP_CHECK_ARG(d->lda % 8 == 0, "gemm: lda=%lld must be a multiple of 8", (long long)d->lda);
+    p.kb_split = K1 / 64;
+    uint64_t dims[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(d->M)};
+    uint64_t str[1] = {static_cast<uint64_t>(d->lda) * 2};
+    uint32_t box[2] = {64, 128};
+    if (encode_tmap_f16(&tmA, d->A, 2, dims, str, box)) return -5;
+    if (d->A2) {
+      SVDPP_CHECK_ARG(d->lda2 % 8 == 0, "gemm: lda2 must be a multiple of 8");
+      uint64_t dims2[2] = {static_cast<uint64_t>(d->K - K1), static_cast<uint64_t>(d->M)};
+      uint64_t str2[1] = {static_cast<uint64_t>(d->lda2) * 2};
+      if (encode_tmap_f16(&tmA2, d->A2, 2, dims2, str2, box)) return -5;
+    } else {
+      tmA2 = tmA;
+    }
+  } else {
+    const int W = d->cW;
+    SVDPP_CHECK_ARG(d->cC % 64 == 0, "gemm: conv C=%d must be a multiple of 64", d->cC);
+    SVDPP_CHECK_ARG((W >= 8 && 128 % W == 0) || W % 128 == 0,
+                    "gemm: conv width %d not tileable by the window path (use svdpp_im2col_nhwc)", W);
+    p.bw = W < 128 ? W : 128;
+    p.nrows = 128 / p.bw;
+    p.cpk = d->cC / 64;
+    uint64_t dims[5] = {static_cast<uint64_t>(d->cC), static_cast<uint64_t>(d->cW), static_cast<uint64_t>(d->cH),
+                        static_cast<uint64_t>(d->cF), static_cast<uint64_t>(d->cB)};
+    uint64_t str[4];
+    str[0] = static_cast<uint64_t>(d->cC) * 2;
+    str[1] = str[0] * d->cW;
+    str[2] = str[1] * d->cH;
+    str[3] = str[2] * d->cF;
+    uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), 1, 1, 1};
+    if (encode_tmap_f16(&tmA, d->A, 5, dims, str, box)) return -5;
+    tmA2 = tmA;
+  }
+  {
+    SVDPP_CHECK_ARG(d->ldw % 8 == 0, "gemm: ldw must be a multiple of 8");
+    uint64_t dims[2] = {static_cast<uint64_t>(d->K), static_cast<uint64_t>(d->N)};
+    uint64_t str[1] = {static_cast<uint64_t>(d->ldw) * 2};
+    uint32_t box[2] = {64, BN};
+    if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
+  }
+  if (d->geglu) return launch_tc<BN, true>(tmA, tmA2, tmB, p, stream);
+  return launch_tc<BN, false>(tmA, tmA2, tmB, p, stream);
+}

@@ -1,0 +1,331 @@
+"""ctypes binding of ``csrc/libsvdpp.so`` — the C ABI declared in ``include/svdpp.h``.
+
+There is no fallback: if the library is missing or a call fails, ``NativeError`` is raised.  Wrappers
+take torch CUDA tensors, pass raw device pointers and the current CUDA stream, and return nothing
+(outputs are caller-allocated), so every call is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+_LIB_PATH = pathlib.Path(__file__).resolve().parent / "csrc" / "libsvdpp.so"
+MAX_TAPS = 9
+GEMM_BN = 160  # N tile of the tcgen05 GEMM; weights are padded / GEGLU-interleaved to it
+
+EXPORTED_SYMBOLS = (
+    "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_gemm_f16",
+    "svdpp_attn_spatial_f16", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
+    "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_sinusoid_embed",
+    "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
+    "svdpp_euler_vpred_step", "svdpp_dummy_unet_step",
+)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("K1", C.c_int32),
+        ("conv", C.c_int32),
+        ("cB", C.c_int32), ("cF", C.c_int32), ("cH", C.c_int32), ("cW", C.c_int32), ("cC", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("taps", (C.c_int8 * 4) * MAX_TAPS),
+        ("Wt", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("rowvec", C.c_void_p), ("rv_ld", C.c_int64),
+        ("rv_hw", C.c_int32), ("rv_div", C.c_int32), ("rv_mod", C.c_int32),
+        ("R1", C.c_void_p), ("ldr1", C.c_int64), ("beta1", C.c_float),
+        ("R2", C.c_void_p), ("ldr2", C.c_int64), ("beta2", C.c_float),
+        ("alpha", C.c_float),
+        ("geglu", C.c_int32),
+        ("D", C.c_void_p), ("ldd", C.c_int64),
+        ("n_store", C.c_int32),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("ld", C.c_int64),
+        ("q_off", C.c_int32), ("k_off", C.c_int32), ("v_off", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("n_img", C.c_int32), ("S", C.c_int32), ("heads", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def library_path() -> pathlib.Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load libsvdpp.so (once). Raises NativeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise NativeError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or library fallback for this path.")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.svdpp_last_error.restype = C.c_char_p
+    lib.svdpp_abi_version.restype = C.c_int
+    lib.svdpp_groupnorm_workspace_bytes.restype = C.c_size_t
+    lib.svdpp_groupnorm_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.svdpp_gemm_f16.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_void_p]
+    lib.svdpp_attn_spatial_f16.argtypes = [C.POINTER(AttnDesc), C.c_int, C.c_void_p]
+    lib.svdpp_attn_temporal_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                            C.c_void_p]
+    lib.svdpp_groupnorm_silu.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.svdpp_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    lib.svdpp_linear_small.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_sinusoid_embed.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p]
+    lib.svdpp_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p]
+    lib.svdpp_im2col_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.svdpp_pack_unet_input.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_float,
+                                          C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_nhwc_to_bfchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p]
+    lib.svdpp_euler_vpred_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                           C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_dummy_unet_step.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p] + \
+        [C.c_int32] * 6 + [C.c_void_p]
+    if lib.svdpp_abi_version() != 1:
+        raise NativeError("libsvdpp.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {load().svdpp_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=torch.float16) -> None:
+    if not t.is_cuda:
+        raise NativeError("native kernels need CUDA tensors (there is no CPU path)")
+    if t.dtype != dtype:
+        raise NativeError(f"expected dtype {dtype}, got {t.dtype}")
+
+
+def device_info() -> Tuple[int, int, int]:
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _check(load().svdpp_device_info(C.byref(a), C.byref(b), C.byref(c)), "svdpp_device_info")
+    return a.value, b.value, c.value
+
+
+# taps ---------------------------------------------------------------------------------------------
+TAPS_3X3 = tuple((kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3))       # K order (kh, kw, c)
+TAPS_T3 = tuple((0, 0, kt - 1) for kt in range(3))                                # K order (kt, c)
+TAPS_1 = ((0, 0, 0),)
+
+
+def _fill_taps(desc: GemmDesc, taps: Sequence[Tuple[int, int, int]]) -> None:
+    desc.ntaps = len(taps)
+    for i, (dw, dh, df) in enumerate(taps):
+        desc.taps[i][0], desc.taps[i][1], desc.taps[i][2], desc.taps[i][3] = dw, dh, df, 0
+
+
+def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=None,
+         conv_dims: Optional[Tuple[int, int, int, int, int]] = None, taps=None,
+         rowvec=None, rv_hw=1, rv_div=1, rv_mod=0, r1=None, beta1=1.0, r2=None, beta2=1.0, alpha=1.0,
+         geglu=False, n_store=0, impl=0) -> torch.Tensor:
+    """``out = epilogue(A @ w.T)``; see ``svdpp_gemm_desc`` in include/svdpp.h.
+
+    ``a``: [M, K] (row stride may exceed K) or, with ``conv_dims=(B,F,H,W,C)``, the contiguous
+    channels-last activation.  ``w``: [N, K] fp16, N a multiple of 160 (GEGLU-interleaved if geglu).
+    """
+    lib = load()
+    d = GemmDesc()
+    for t in (out, a, w):
+        _req(t)
+    N, K = w.shape
+    d.N, d.K = N, K
+    d.Wt, d.ldw = w.data_ptr(), w.stride(0)
+    if conv_dims is not None:
+        B_, F_, H_, W_, C_ = conv_dims
+        d.conv = 1
+        d.cB, d.cF, d.cH, d.cW, d.cC = B_, F_, H_, W_, C_
+        _fill_taps(d, taps)
+        d.M = B_ * F_ * H_ * W_
+        if not a.is_contiguous():
+            raise NativeError("conv-mode activation must be contiguous")
+        d.A, d.lda = a.data_ptr(), C_
+    else:
+        d.conv = 0
+        d.M = a.shape[0]
+        d.A, d.lda = a.data_ptr(), a.stride(0)
+        if a2 is not None:
+            _req(a2)
+            d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), a.shape[1]
+    d.bias = _ptr(bias)
+    if rowvec is not None:
+        d.rowvec, d.rv_ld = rowvec.data_ptr(), rowvec.stride(0)
+        d.rv_hw, d.rv_div, d.rv_mod = rv_hw, rv_div, rv_mod
+    if r1 is not None:
+        d.R1, d.ldr1, d.beta1 = r1.data_ptr(), r1.stride(0), beta1
+    if r2 is not None:
+        d.R2, d.ldr2, d.beta2 = r2.data_ptr(), r2.stride(0), beta2
+    d.alpha = alpha
+    d.geglu = 1 if geglu else 0
+    d.D, d.ldd = out.data_ptr(), out.stride(0)
+    d.n_store = n_store
+    _check(lib.svdpp_gemm_f16(C.byref(d), impl, _stream()), "svdpp_gemm_f16")
+    return out
+
+
+def attn_spatial(out: torch.Tensor, qkv: torch.Tensor, *, n_img: int, S: int, heads: int,
+                 q_off: int, k_off: int, v_off: int, scale: float, impl=0) -> torch.Tensor:
+    _req(out), _req(qkv)
+    d = AttnDesc()
+    d.qkv, d.ld = qkv.data_ptr(), qkv.stride(0)
+    d.q_off, d.k_off, d.v_off = q_off, k_off, v_off
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.n_img, d.S, d.heads, d.scale = n_img, S, heads, scale
+    _check(load().svdpp_attn_spatial_f16(C.byref(d), impl, _stream()), "svdpp_attn_spatial_f16")
+    return out
+
+
+def attn_temporal(out: torch.Tensor, qkv: torch.Tensor, *, B: int, F: int, HW: int, heads: int,
+                  q_off: int, k_off: int, v_off: int, scale: float) -> torch.Tensor:
+    _req(out), _req(qkv)
+    _check(load().svdpp_attn_temporal_f16(qkv.data_ptr(), qkv.stride(0), q_off, k_off, v_off, out.data_ptr(),
+                                          out.stride(0), B, F, HW, heads, scale, _stream()),
+           "svdpp_attn_temporal_f16")
+    return out
+
+
+def groupnorm_workspace_bytes(n_img: int, HW: int) -> int:
+    return int(load().svdpp_groupnorm_workspace_bytes(n_img, HW))
+
+
+def groupnorm_silu(out, x1, gamma, beta, *, n_img, HW, eps, silu=True, x2=None, frames_per_stat=1,
+                   workspace: torch.Tensor) -> torch.Tensor:
+    _req(out), _req(x1)
+    C1 = x1.shape[-1]
+    C2 = 0 if x2 is None else x2.shape[-1]
+    _check(load().svdpp_groupnorm_silu(x1.data_ptr(), C1, _ptr(x2), C2, gamma.data_ptr(), beta.data_ptr(),
+                                       out.data_ptr(), n_img, HW, frames_per_stat, eps, 1 if silu else 0,
+                                       workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                       _stream()), "svdpp_groupnorm_silu")
+    return out
+
+
+def layernorm(out, x, gamma, beta, *, eps=1e-5, addvec=None, add_hw=1, add_mod=1) -> torch.Tensor:
+    _req(out), _req(x)
+    M, Cc = x.shape
+    _check(load().svdpp_layernorm(x.data_ptr(), x.stride(0), _ptr(addvec), add_hw, add_mod, gamma.data_ptr(),
+                                  beta.data_ptr(), out.data_ptr(), out.stride(0), M, Cc, eps, _stream()),
+           "svdpp_layernorm")
+    return out
+
+
+def linear_small(out, x, w, bias=None, *, x_add=None, act_in=0, act_out=0) -> torch.Tensor:
+    _req(out), _req(x), _req(w)
+    R, K = x.shape
+    N = w.shape[0]
+    if x_add is not None and (x_add.stride(0) != x.stride(0) or x_add.shape != x.shape):
+        raise NativeError("linear_small: x_add must match x")
+    _check(load().svdpp_linear_small(x.data_ptr(), _ptr(x_add), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                     out.data_ptr(), out.stride(0), R, N, K, act_in, act_out, _stream()),
+           "svdpp_linear_small")
+    return out
+
+
+def sinusoid_embed(out, src: Optional[torch.Tensor], *, n_vals: int, dim: int, src_mod: int = 0) -> torch.Tensor:
+    _req(out)
+    if src is None:
+        kind = 2
+    elif src.dtype == torch.float32:
+        kind = 0
+    elif src.dtype == torch.float16:
+        kind = 1
+    else:
+        raise NativeError("sinusoid_embed: src must be fp32 or fp16")
+    _check(load().svdpp_sinusoid_embed(_ptr(src), kind, src_mod, n_vals, dim, out.data_ptr(), _stream()),
+           "svdpp_sinusoid_embed")
+    return out
+
+
+def upsample2x(out, x, *, n_img, H, W, Cc) -> torch.Tensor:
+    _req(out), _req(x)
+    _check(load().svdpp_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), n_img, H, W, Cc, _stream()),
+           "svdpp_upsample2x_nhwc")
+    return out
+
+
+def im2col(out, x, *, B, F, H, W, Cc, Ho, Wo, stride, taps) -> torch.Tensor:
+    _req(out), _req(x)
+    arr = (C.c_int8 * (4 * len(taps)))()
+    for i, (dw, dh, df) in enumerate(taps):
+        arr[4 * i], arr[4 * i + 1], arr[4 * i + 2], arr[4 * i + 3] = dw, dh, df, 0
+    _check(load().svdpp_im2col_nhwc(x.data_ptr(), out.data_ptr(), out.stride(0), B, F, H, W, Cc, Ho, Wo, stride,
+                                    len(taps), C.cast(arr, C.c_void_p), _stream()), "svdpp_im2col_nhwc")
+    return out
+
+
+def pack_unet_input(out, src0, strides0, C0, in_div, src1, strides1, C1, *, B, F, H, W,
+                    out_bfchw: bool = False) -> torch.Tensor:
+    _req(out), _req(src0)
+    s1 = strides1 if src1 is not None else (0, 0, 0)
+    _check(load().svdpp_pack_unet_input(src0.data_ptr(), strides0[0], strides0[1], strides0[2], C0, in_div,
+                                        _ptr(src1), s1[0], s1[1], s1[2], C1, out.data_ptr(),
+                                        1 if out_bfchw else 0, B, F, H, W, _stream()), "svdpp_pack_unet_input")
+    return out
+
+
+def nhwc_to_bfchw(out, x, *, B, F, Cc, H, W) -> torch.Tensor:
+    _req(out), _req(x)
+    _check(load().svdpp_nhwc_to_bfchw(x.data_ptr(), out.data_ptr(), B, F, Cc, H, W, _stream()),
+           "svdpp_nhwc_to_bfchw")
+    return out
+
+
+def euler_vpred_step(out, latent, v_a, *, v_cond=None, gs=None, v_nhwc: bool, c_v: float, c_x: float,
+                     sigma: float, dt: float) -> torch.Tensor:
+    _req(out), _req(latent), _req(v_a)
+    B, Cc, F, H, W = latent.shape
+    _check(load().svdpp_euler_vpred_step(latent.data_ptr(), v_a.data_ptr(), _ptr(v_cond), _ptr(gs),
+                                         1 if v_nhwc else 0, c_v, c_x, sigma, dt, out.data_ptr(), B, Cc, F, H, W,
+                                         _stream()), "svdpp_euler_vpred_step")
+    return out
+
+
+def dummy_unet_step(out, x, w1, b1, w2, b2, ln_g, ln_b, ln_eps, tanh_scale, hidden_ws) -> torch.Tensor:
+    for t in (out, x, w1, b1, w2, b2, hidden_ws):
+        _req(t, torch.float32)
+    B, Cc, F, H, W = x.shape
+    Ch = w1.shape[0]
+    _check(load().svdpp_dummy_unet_step(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                        _ptr(ln_g), _ptr(ln_b), ln_eps, tanh_scale, hidden_ws.data_ptr(),
+                                        out.data_ptr(), B, Cc, Ch, F, H, W, _stream()), "svdpp_dummy_unet_step")
+    return out

@@ -1,0 +1,219 @@
+"""Stage runner for diffusion-step pipeline parallelism.
+
+Interface of reference ``src/pipeline/pipeline.py`` (``LatentSpec`` :25-34, ``PipelineConfig`` :37-48,
+``PipelineStage`` :54-157, ``run_single_latent`` :160-185, ``run_pipeline_latents`` :188-208): every rank
+holds the whole model, owns a contiguous slice of the step schedule, receives the latent from
+``rank-1``, runs ``model(latent, timesteps[i])`` for its slice and sends the latent to ``rank+1``.
+
+What differs from the reference is *how* the handoff is issued, not what is exchanged:
+
+* the receive buffer is a persistent pair (``LatentSpec.empty`` once per slot, reference allocates per
+  sample at ``pipeline.py:76``);
+* ``run_many`` pre-posts the receive for sample ``k+1`` before computing sample ``k`` and sends with
+  ``isend``, so on NCCL the 1.8 MB latent crosses NVLink while the stage computes (the reference's
+  blocking ``send``/``recv`` pair at ``pipeline.py:78,84`` serialises them on gloo);
+* ``PipelineConfig.allow_uneven`` opts into ``assign_steps_uneven`` (the reference raises, Q1).
+
+Message order, tags, shapes and the values exchanged are identical, so a mixed world of reference
+and new stages interoperates.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from collections.abc import Sequence
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .step_assignment import StepRange, assign_steps, assign_steps_uneven
+
+LOGGER = logging.getLogger(__name__)
+
+
+@dataclass(frozen=True)
+class LatentSpec:
+    """Shape/dtype/device every stage agrees on out of band (reference ``pipeline.py:25-34``)."""
+
+    shape: torch.Size
+    dtype: torch.dtype
+    device: torch.device
+
+    def empty(self) -> torch.Tensor:
+        return torch.empty(self.shape, dtype=self.dtype, device=self.device)
+
+
+@dataclass(frozen=True)
+class PipelineConfig:
+    total_steps: int
+    world_size: int
+    rank: int
+    timesteps: Sequence[int]
+    latent_spec: LatentSpec
+    send_tag: int = 0
+    allow_uneven: bool = False  # extension: reference rejects total_steps % world_size != 0
+
+    def __post_init__(self) -> None:
+        if len(self.timesteps) != self.total_steps:
+            raise ValueError("len(timesteps) must equal total_steps.")
+
+
+InputSupplier = Callable[[int], torch.Tensor]
+
+
+class PipelineStage:
+    """One rank of the step pipeline."""
+
+    def __init__(self, model, config: PipelineConfig, logger: Optional[logging.Logger] = None) -> None:
+        self.model = model
+        self.config = config
+        self.logger = logger or LOGGER
+        split = assign_steps_uneven if config.allow_uneven else assign_steps
+        self.step_range: StepRange = split(
+            total_steps=config.total_steps, world_size=config.world_size, rank=config.rank
+        )
+        self._local_timesteps: List[int] = list(
+            config.timesteps[self.step_range.start: self.step_range.end]
+        )
+        self._recv_slots: List[Optional[torch.Tensor]] = [None, None]
+        self._recv_turn = 0
+        self._pending_send = None  # (work handle, tensor kept alive)
+
+    # ------------------------------------------------------------------ logging
+    def _log(self, message: str) -> None:
+        if self.logger.isEnabledFor(logging.INFO):
+            self.logger.info("[rank=%s] %s", self.config.rank, message)
+
+    # ------------------------------------------------------------------ comm
+    def _next_recv_slot(self) -> torch.Tensor:
+        i = self._recv_turn
+        self._recv_turn ^= 1
+        if self._recv_slots[i] is None:
+            self._recv_slots[i] = self.config.latent_spec.empty()
+        return self._recv_slots[i]
+
+    def _post_recv(self):
+        buf = self._next_recv_slot()
+        work = dist.irecv(buf, src=self.config.rank - 1, tag=self.config.send_tag)
+        return work, buf
+
+    def _recv_latent(self) -> torch.Tensor:
+        """Blocking receive from ``rank-1`` (reference ``pipeline.py:75-80``)."""
+        self._log(f"waiting for latent from rank {self.config.rank - 1}")
+        work, buf = self._post_recv()
+        work.wait()
+        self._log("received latent")
+        return buf
+
+    def _drain_send(self) -> None:
+        if self._pending_send is not None:
+            self._pending_send[0].wait()
+            self._pending_send = None
+
+    def _send_latent(self, latent: torch.Tensor, *, blocking: bool = True) -> None:
+        """Send to ``rank+1`` (reference ``pipeline.py:82-84``)."""
+        self._log(f"sending latent to rank {self.config.rank + 1}")
+        self._drain_send()
+        if blocking:
+            dist.send(latent, dst=self.config.rank + 1, tag=self.config.send_tag)
+        else:
+            work = dist.isend(latent, dst=self.config.rank + 1, tag=self.config.send_tag)
+            self._pending_send = (work, latent)
+
+    # ------------------------------------------------------------------ compute
+    def _run_local_steps(self, latent: torch.Tensor) -> torch.Tensor:
+        """The inner hot loop (reference ``pipeline.py:86-98``): ``model(latent, timesteps[i])``."""
+        if len(self._local_timesteps) != self.step_range.count:
+            raise RuntimeError("Local timestep slice length mismatch with step range.")
+        verbose = self.logger.isEnabledFor(logging.INFO)
+        for step in self._local_timesteps:
+            t0 = time.time() if verbose else 0.0
+            latent = self.model(latent, step)
+            if verbose:
+                self._log(f"step {step} completed in {(time.time() - t0) * 1000.0:.2f} ms")
+        return latent
+
+    # ------------------------------------------------------------------ public API
+    def run(self, input_latent: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """One latent through this stage; returns it on the last rank, else ``None``."""
+        return self._process_single_latent(input_latent, sample_idx=None)
+
+    def run_many(self, num_samples: int, *, input_supplier: Optional[InputSupplier] = None
+                 ) -> Optional[List[torch.Tensor]]:
+        if num_samples <= 0:
+            raise ValueError("num_samples must be positive for pipeline execution")
+        cfg = self.config
+        if cfg.rank == 0 and input_supplier is None:
+            raise ValueError("rank 0 requires an input_supplier when processing multiple samples")
+        last = cfg.rank == cfg.world_size - 1
+        outputs: List[torch.Tensor] = []
+        pending = self._post_recv() if cfg.rank > 0 else None
+        for sample_idx in range(num_samples):
+            if cfg.rank == 0:
+                latent = input_supplier(sample_idx)
+                if latent is None:
+                    raise ValueError("rank 0 requires an input latent tensor")
+                latent = latent.to(cfg.latent_spec.device)
+            else:
+                work, buf = pending
+                work.wait()
+                # the slot is rewritten two samples later; the model returns a fresh tensor per
+                # step, but an empty stage would forward the slot itself, hence the clone there
+                latent = buf if self.step_range.count else buf.clone()
+                pending = self._post_recv() if sample_idx + 1 < num_samples else None
+            latent = self._run_local_steps(latent)
+            if last:
+                outputs.append(latent)
+            else:
+                self._send_latent(latent, blocking=False)
+        self._drain_send()
+        return outputs if outputs else None
+
+    def _process_single_latent(self, input_latent: Optional[torch.Tensor],
+                               sample_idx: Optional[int]) -> Optional[torch.Tensor]:
+        """recv -> local steps -> send for one sample (reference ``pipeline.py:134-157``; called
+        directly by the reference's benchmark mode, so its name and signature are kept)."""
+        cfg = self.config
+        prefix = f"sample {sample_idx} " if sample_idx is not None else ""
+        if cfg.rank == 0:
+            if input_latent is None:
+                raise ValueError("rank 0 requires an input latent tensor")
+            latent = input_latent.to(cfg.latent_spec.device)
+            self._log(f"{prefix}input prepared")
+        else:
+            if input_latent is not None:
+                raise ValueError("non-zero ranks should not receive an eager latent")
+            latent = self._recv_latent()
+            self._log(f"{prefix}received latent")
+
+        latent = self._run_local_steps(latent)
+
+        if cfg.rank == cfg.world_size - 1:
+            self._log(f"{prefix}final rank completed")
+            return latent
+        self._send_latent(latent, blocking=True)
+        return None
+
+
+def run_single_latent(model, *, total_steps: int, timesteps: Sequence[int], world_size: int,
+                      rank: int, latent_spec: LatentSpec, input_latent: Optional[torch.Tensor],
+                      logger: Optional[logging.Logger] = None, allow_uneven: bool = False
+                      ) -> Optional[torch.Tensor]:
+    """All ranks call this once per latent; rank 0 passes the input (reference ``pipeline.py:160``)."""
+    config = PipelineConfig(total_steps=total_steps, world_size=world_size, rank=rank,
+                            timesteps=timesteps, latent_spec=latent_spec, allow_uneven=allow_uneven)
+    return PipelineStage(model=model, config=config, logger=logger).run(input_latent=input_latent)
+
+
+def run_pipeline_latents(model, *, total_steps: int, timesteps: Sequence[int], world_size: int,
+                         rank: int, latent_spec: LatentSpec, num_samples: int,
+                         input_supplier: Optional[InputSupplier],
+                         logger: Optional[logging.Logger] = None, allow_uneven: bool = False
+                         ) -> Optional[List[torch.Tensor]]:
+    """Stream ``num_samples`` latents through the pipeline (reference ``pipeline.py:188-208``)."""
+    config = PipelineConfig(total_steps=total_steps, world_size=world_size, rank=rank,
+                            timesteps=timesteps, latent_spec=latent_spec, allow_uneven=allow_uneven)
+    return PipelineStage(model=model, config=config, logger=logger).run_many(
+        num_samples, input_supplier=input_supplier)
