@@ -1,0 +1,392 @@
+"""Kernel-level parity checks: each function runs one libsvdpp.so entry point on the GPU and compares it
+with the same op written in plain torch (fp32 math on the same fp16 inputs).  Used by the pytest GPU
+tests and by tools/gpu_check.py (which runs every check in its own process and logs the numbers).
+
+Each check returns a dict with at least {"max_err", "tol", "ok"}.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+import vdpp_b200  # noqa: F401
+from vdpp_b200 import native
+from vdpp_b200.models.native_unet import interleave_geglu
+
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=None):
+    g = torch.Generator(device=DEV)
+    g.manual_seed(0 if seed is None else seed)
+    return (torch.randn(*shape, device=DEV, generator=g) * scale).half()
+
+
+def _cmp(got: torch.Tensor, ref: torch.Tensor, rel=2e-3, floor=1e-3):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    tol = rel * ref.abs().max().item() + floor
+    cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    finite = bool(torch.isfinite(got).all())
+    return dict(max_err=err, tol=tol, cos=cos, ref_absmax=ref.abs().max().item(), ok=bool(finite and err <= tol))
+
+
+def _pad_n(w, mult=native.GEMM_BN):
+    n = w.shape[0]
+    npad = (n + mult - 1) // mult * mult
+    if npad == n:
+        return w.contiguous()
+    out = torch.zeros((npad,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+    out[:n] = w
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm_linear(M=300, N=320, K=320, impl=0, epilogue="full", split=False):
+    a = _rand(M, K, seed=1)
+    w = _rand(N, K, scale=K ** -0.5, seed=2)
+    bias = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    kw = dict(bias=_pad_n(bias))
+    ref = a.float() @ w.float().t() + bias.float()
+    if epilogue == "full":
+        hw, div, mod = 7, 2, 5
+        rv = _rand(mod, N, seed=4)
+        r1, r2 = _rand(M, N, seed=5), _rand(M, N, seed=6)
+        rows = (torch.arange(M, device=DEV) // hw // div) % mod
+        ref = 0.75 * (ref + rv.float()[rows]) + 0.5 * r1.float() - 1.25 * r2.float()
+        kw.update(rowvec=rv, rv_hw=hw, rv_div=div, rv_mod=mod, r1=r1, beta1=0.5, r2=r2, beta2=-1.25, alpha=0.75)
+    if split:
+        k1 = (K // 2) // 64 * 64
+        a1, a2 = a[:, :k1].contiguous(), a[:, k1:].contiguous()
+        native.gemm(out, a1, _pad_n(w), a2=a2, n_store=N, impl=impl, **kw)
+    else:
+        native.gemm(out, a, _pad_n(w), n_store=N, impl=impl, **kw)
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def gemm_geglu(M=260, C=128, impl=0):
+    inner = 4 * C
+    a = _rand(M, C, seed=1)
+    w = _rand(2 * inner, C, scale=C ** -0.5, seed=2)
+    b = _rand(2 * inner, scale=0.1, seed=3)
+    wi, bi, n = interleave_geglu(w, b)
+    out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.float16)
+    native.gemm(out, a, wi, bias=bi, geglu=True, n_store=inner, impl=impl)
+    y = (a.float() @ w.float().t() + b.float()).half()
+    val, gate = y.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    torch.cuda.synchronize()
+    return _cmp(out, ref, rel=4e-3)
+
+
+def conv3x3(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
+    x = _rand(B * Fr, H, W, C, seed=1)                      # channels-last
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    b = _rand(Cout, seed=3)
+    wk = _pad_n(w.permute(0, 2, 3, 1).reshape(Cout, -1))
+    out = torch.full((B * Fr * H * W, Cout), float("nan"), device=DEV, dtype=torch.float16)
+    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_3X3,
+                n_store=Cout, impl=impl)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    return _cmp(out, ref.reshape(-1, Cout))
+
+
+def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
+    x = _rand(B, Fr, H, W, C, seed=1)
+    w = _rand(C, C, 3, 1, 1, scale=(3 * C) ** -0.5, seed=2)
+    b = _rand(C, seed=3)
+    wk = _pad_n(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(C, -1))
+    out = torch.full((B * Fr * H * W, C), float("nan"), device=DEV, dtype=torch.float16)
+    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_T3,
+                n_store=C, impl=impl)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3).float(), w.float(), b.float(), padding=(1, 0, 0)).permute(0, 2, 3, 4, 1)
+    torch.cuda.synchronize()
+    return _cmp(out, ref.reshape(-1, C))
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_spatial(n_img=2, S=320, heads=2, impl=0):
+    C = heads * 64
+    qkv = _rand(n_img * S, 3 * C, seed=1)
+    out = torch.full((n_img * S, C), float("nan"), device=DEV, dtype=torch.float16)
+    native.attn_spatial(out, qkv, n_img=n_img, S=S, heads=heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125,
+                        impl=impl)
+    q, k, v = [t.reshape(n_img, S, heads, 64).transpose(1, 2).float() for t in qkv.split(C, dim=1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_img * S, C)
+    torch.cuda.synchronize()
+    return _cmp(out, ref, rel=4e-3)
+
+
+def attn_temporal(B=2, Fr=5, HW=24, heads=2):
+    C = heads * 64
+    qkv = _rand(B * Fr * HW, 3 * C, seed=1)
+    out = torch.full((B * Fr * HW, C), float("nan"), device=DEV, dtype=torch.float16)
+    native.attn_temporal(out, qkv, B=B, F=Fr, HW=HW, heads=heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125)
+    t = qkv.reshape(B, Fr, HW, 3, heads, 64).permute(3, 0, 2, 4, 1, 5).float()   # [3, B, HW, heads, F, 64]
+    ref = F.scaled_dot_product_attention(t[0], t[1], t[2])                       # [B, HW, heads, F, 64]
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(B * Fr * HW, C)
+    torch.cuda.synchronize()
+    return _cmp(out, ref, rel=4e-3)
+
+
+# ------------------------------------------------------------------------------------------ norms
+def groupnorm(n_img=4, HW=100, C1=64, C2=0, fps=1, silu=True, eps=1e-5):
+    x1 = _rand(n_img * HW, C1, seed=1) * 2 + 0.5
+    x2 = _rand(n_img * HW, C2, seed=2) if C2 else None
+    C = C1 + C2
+    g, b = _rand(C, seed=3), _rand(C, seed=4)
+    out = torch.full((n_img * HW, C), float("nan"), device=DEV, dtype=torch.float16)
+    ws = torch.empty(native.groupnorm_workspace_bytes(n_img, HW) // 4 + 1, dtype=torch.float32, device=DEV)
+    native.groupnorm_silu(out, x1, g, b, n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2, frames_per_stat=fps,
+                          workspace=ws)
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+    xr = x.float().reshape(n_img // fps, fps * HW, C).permute(0, 2, 1)     # [stat, C, L]
+    ref = F.group_norm(xr, 32, g.float(), b.float(), eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(n_img * HW, C)
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def layernorm(M=70, C=320, add=True):
+    x = _rand(M, C, seed=1) * 3 + 1
+    g, b = _rand(C, seed=2), _rand(C, seed=3)
+    hw, mod = 4, 5
+    av = _rand(mod, C, seed=4) if add else None
+    out = torch.full((M, C), float("nan"), device=DEV, dtype=torch.float16)
+    native.layernorm(out, x, g, b, addvec=av, add_hw=hw, add_mod=mod)
+    xin = x
+    if add:
+        rows = (torch.arange(M, device=DEV) // hw) % mod
+        xin = x + av[rows]
+    ref = F.layer_norm(xin.float(), (C,), g.float(), b.float(), 1e-5)
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def linear_small(R=3, N=100, K=256):
+    x, xa = _rand(R, K, seed=1), _rand(R, K, seed=2)
+    w, b = _rand(N, K, scale=K ** -0.5, seed=3), _rand(N, seed=4)
+    out = torch.full((R, N), float("nan"), device=DEV, dtype=torch.float16)
+    native.linear_small(out, x, w, b, x_add=xa, act_in=1, act_out=1)
+    ref = F.silu(F.linear(F.silu(x + xa).float(), w.float(), b.float()).half().float())
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def sinusoid(dim=320):
+    from oracle.unet_torch import timestep_embedding
+    t = torch.tensor([1.6377, -1.5536, 0.3], device=DEV)
+    o0 = native.sinusoid_embed(torch.empty(3, dim, device=DEV, dtype=torch.float16), t, n_vals=3, dim=dim)
+    r0 = timestep_embedding(t, dim)
+    ids = torch.tensor([5.0, 127.0, 0.02], device=DEV).half()
+    o1 = native.sinusoid_embed(torch.empty(3, 256, device=DEV, dtype=torch.float16), ids, n_vals=3, dim=256)
+    r1 = timestep_embedding(ids, 256)
+    o2 = native.sinusoid_embed(torch.empty(6, dim, device=DEV, dtype=torch.float16), None, n_vals=6, dim=dim, src_mod=3)
+    r2 = timestep_embedding(torch.arange(3, device=DEV).repeat(2), dim)
+    torch.cuda.synchronize()
+    res = [_cmp(o0, r0, rel=1e-3), _cmp(o1, r1, rel=1e-3), _cmp(o2, r2, rel=1e-3)]
+    return dict(max_err=max(r["max_err"] for r in res), tol=res[0]["tol"], ok=all(r["ok"] for r in res))
+
+
+# ------------------------------------------------------------------------------------------ data movement
+def movers():
+    B, Fr, H, W, C = 2, 3, 6, 10, 16
+    x = _rand(B * Fr, H, W, C, seed=1)
+    up = native.upsample2x(torch.empty(B * Fr, 2 * H, 2 * W, C, device=DEV, dtype=torch.float16), x, n_img=B * Fr,
+                           H=H, W=W, Cc=C)
+    ref_up = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    parts = dict(upsample=torch.equal(up.float(), ref_up))
+    ok = True
+    for stride in (1, 2):
+        Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+        ldo = 9 * C + 16
+        cols = torch.full((B * Fr * Ho * Wo, ldo), float("nan"), device=DEV, dtype=torch.float16)
+        native.im2col(cols, x, B=B, F=Fr, H=H, W=W, Cc=C, Ho=Ho, Wo=Wo, stride=stride, taps=native.TAPS_3X3)
+        unf = F.unfold(x.permute(0, 3, 1, 2).float(), 3, padding=1, stride=stride)      # [n, C*9, L], (c, kh, kw)
+        unf = unf.reshape(B * Fr, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(-1, 9 * C)  # (kh, kw, c)
+        parts[f"im2col_s{stride}"] = torch.equal(cols[:, :9 * C].float(), unf) and bool((cols[:, 9 * C:] == 0).all())
+    lat = _rand(B, 4, Fr, H, W, seed=2) * 50
+    img = _rand(B, 4, Fr, H, W, seed=3)
+    st = (4 * Fr * H * W, H * W, Fr * H * W)
+    div = 3.3
+    for bfchw in (False, True):
+        shape = (B, Fr, 8, H, W) if bfchw else (B * Fr, H, W, 8)
+        o = native.pack_unet_input(torch.empty(shape, device=DEV, dtype=torch.float16), lat, st, 4, div, img, st, 4,
+                                   B=B, F=Fr, H=H, W=W, out_bfchw=bfchw)
+        ref = torch.cat([(lat.float() / div).half(), img], dim=1).permute(0, 2, 1, 3, 4)   # [B,F,8,H,W]
+        if not bfchw:
+            ref = ref.permute(0, 1, 3, 4, 2).reshape(B * Fr, H, W, 8)
+        parts[f"pack_bfchw{int(bfchw)}"] = torch.equal(o, ref.half())
+        parts[f"pack_bfchw{int(bfchw)}_err"] = (o.float() - ref.float()).abs().max().item()
+    v = _rand(B * Fr * H * W, 4, seed=4)
+    o = native.nhwc_to_bfchw(torch.empty(B, Fr, 4, H, W, device=DEV, dtype=torch.float16), v, B=B, F=Fr, Cc=4, H=H, W=W)
+    parts["nhwc_to_bfchw"] = torch.equal(o, v.reshape(B, Fr, H, W, 4).permute(0, 1, 4, 2, 3))
+    torch.cuda.synchronize()
+    ok = all(bool(v_) for k_, v_ in parts.items() if not k_.endswith("_err"))
+    return dict(max_err=0.0 if ok else 1.0, tol=0.0, ok=bool(ok), **parts)
+
+
+def euler(cfg=True, step=3, n=25):
+    """Bit-exact against the oracle's restatement of svd_unet.py:410-439 (given the same UNet output)."""
+    from oracle.scheduler import euler_karras_tables
+    from vdpp_b200.models import scheduler as sched
+    B, Fr, H, W = 1, 5, 8, 12
+    sig, _, _ = euler_karras_tables(n)
+    lat = _rand(B, 4, Fr, H, W, seed=1) * float(sig[step])
+    u, c = _rand(B, Fr, 4, H, W, seed=2), _rand(B, Fr, 4, H, W, seed=3)
+    gs = torch.linspace(1.0, 3.0, Fr).view(1, 1, Fr, 1, 1).to(DEV, dtype=torch.float16)
+    sigma, sigma_next = sig[step].to(DEV), sig[step + 1].to(DEV)
+    v = u + gs.permute(0, 2, 1, 3, 4) * (c - u) if cfg else u
+    vf = v.permute(0, 2, 1, 3, 4).float()
+    x = lat.float()
+    s = sigma.float()
+    x0 = vf * (-s / (s ** 2 + 1) ** 0.5) + x / (s ** 2 + 1)
+    d = (x - x0) / s
+    ref = (x + d * (float(sigma_next) - float(sigma))).half()
+    _, c_v, c_x, s_h, dt = sched.step_coefficients(sig.numpy(), step)
+    ok = True
+    for nhwc in (False, True):
+        ua = u.permute(0, 1, 3, 4, 2).contiguous() if nhwc else u
+        ca = c.permute(0, 1, 3, 4, 2).contiguous() if nhwc else c
+        out = native.euler_vpred_step(torch.empty_like(lat), lat, ua, v_cond=ca if cfg else None,
+                                      gs=gs.reshape(-1).contiguous() if cfg else None, v_nhwc=nhwc, c_v=c_v, c_x=c_x,
+                                      sigma=s_h, dt=dt)
+        ok = ok and torch.equal(out, ref)
+        err = (out.float() - ref.float()).abs().max().item()
+    torch.cuda.synchronize()
+    return dict(max_err=err, tol=0.0, ok=bool(ok))
+
+
+def dummy_unet(C=4, Ch=16, step=7):
+    from vdpp_b200.models import DummyUNet
+    torch.manual_seed(0)
+    m = DummyUNet(channels=C, hidden_channels=Ch).to(DEV)
+    x = torch.randn(1, C, 6, 16, 16, device=DEV)
+    with torch.no_grad():
+        ref = m(x, step)
+    hid = torch.empty(1, Ch, 6, 16, 16, device=DEV)
+    out = native.dummy_unet_step(torch.empty_like(x), x, m.net[0].weight.contiguous(), m.net[0].bias,
+                                 m.net[2].weight.contiguous(), m.net[2].bias, m.norm.weight, m.norm.bias, m.norm.eps,
+                                 math.tanh(step / 10.0), hid)
+    torch.cuda.synchronize()
+    return _cmp(out, ref, rel=1e-4, floor=1e-4)
+
+
+ALL_CHECKS = {
+    "movers": lambda: movers(),
+    "euler_cfg": lambda: euler(True),
+    "euler_nocfg": lambda: euler(False),
+    "sinusoid": lambda: sinusoid(),
+    "linear_small": lambda: linear_small(),
+    "layernorm": lambda: layernorm(),
+    "layernorm_1280": lambda: layernorm(M=33, C=1280, add=False),
+    "groupnorm": lambda: groupnorm(),
+    "groupnorm_cat": lambda: groupnorm(n_img=2, HW=144, C1=128, C2=64),
+    "groupnorm_temporal": lambda: groupnorm(n_img=6, HW=50, C1=320, fps=3, eps=1e-6, silu=False),
+    "attn_temporal": lambda: attn_temporal(),
+    "attn_temporal_25": lambda: attn_temporal(B=1, Fr=25, HW=9, heads=5),
+    "dummy_unet": lambda: dummy_unet(),
+    "simt_gemm_linear": lambda: gemm_linear(impl=1),
+    "simt_gemm_split": lambda: gemm_linear(impl=1, K=384, split=True),
+    "simt_gemm_geglu": lambda: gemm_geglu(impl=1),
+    "simt_conv3x3": lambda: conv3x3(impl=1),
+    "simt_conv_temporal": lambda: conv_temporal(impl=1),
+    "simt_attn_spatial": lambda: attn_spatial(impl=1),
+    "tc_gemm_plain": lambda: gemm_linear(M=256, N=160, K=64, impl=0, epilogue="bias"),
+    "tc_gemm_linear": lambda: gemm_linear(impl=0),
+    "tc_gemm_big": lambda: gemm_linear(M=4000, N=640, K=1280, impl=0),
+    "tc_gemm_split": lambda: gemm_linear(impl=0, K=384, split=True),
+    "tc_gemm_geglu": lambda: gemm_geglu(impl=0),
+    "tc_gemm_geglu_320": lambda: gemm_geglu(M=1000, C=320, impl=0),
+    "tc_conv3x3_w32": lambda: conv3x3(impl=0),
+    "tc_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=160, impl=0),
+    "tc_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=64, impl=0),
+    "tc_conv_temporal": lambda: conv_temporal(impl=0),
+    "tc_attn_spatial_256": lambda: attn_spatial(n_img=1, S=256, heads=1, impl=0),
+    "tc_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=0),
+    "tc_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=0),
+    "tc_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=0),
+}
+
+
+# ------------------------------------------------------------------------------------------ whole UNet
+def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=0, seed=0):
+    from oracle.unet_torch import UNetSpatioTemporalConditionModel, tiny_config
+    from vdpp_b200.models.native_unet import NativeUNet
+    cfg = tiny_config(**(cfg_over or {}))
+    torch.manual_seed(seed)
+    oracle = UNetSpatioTemporalConditionModel(**cfg).to(DEV).half().eval()
+    nat = NativeUNet(oracle.state_dict(), config=oracle.config, device=DEV, gemm_impl=gemm_impl, attn_impl=attn_impl)
+    return oracle, nat
+
+
+def unet_tiny(gemm_impl=0, attn_impl=0, B=1, Fr=3, H=16, W=16, cfg_over=None):
+    """NativeUNet vs the torch oracle (fp16 library kernels) and vs the oracle in fp32, same weights."""
+    oracle, nat = _tiny_pair(cfg_over, gemm_impl, attn_impl)
+    g = torch.Generator(device=DEV)
+    g.manual_seed(1)
+    sample = torch.randn(B, Fr, 8, H, W, device=DEV, generator=g).half()
+    enc = torch.randn(B, 1, 1024, device=DEV, generator=g).half()
+    ids = torch.tensor([[5.0, 127.0, 0.02]], device=DEV).half().repeat(B, 1)
+    t = torch.tensor(1.6377)
+    with torch.no_grad():
+        ref16 = oracle(sample, t, enc, ids)[0]
+        ref32 = oracle.float()(sample.float(), t, enc.float(), ids.float())[0]
+        oracle.half()
+    got = nat(sample, t, enc, ids)[0]
+    torch.cuda.synchronize()
+    r = _cmp(got, ref32, rel=2e-2, floor=2e-3)
+    floor16 = (ref16.float() - ref32).abs().max().item()
+    r["lib_fp16_vs_fp32"] = floor16
+    r["native_vs_lib_fp16"] = (got.float() - ref16.float()).abs().max().item()
+    # native must be about as close to the fp32 truth as the library fp16 path is
+    r["ok"] = bool(r["ok"] and r["max_err"] <= max(4 * floor16, 5e-3))
+    return r
+
+
+def svd_steps(n_steps=4, total=25, cfg_scale=None, gemm_impl=0, attn_impl=0, B=1, Fr=3, H=16, W=16, graph=False):
+    """StableVideoUNet (native) vs the oracle restatement of the reference wrapper, a few Euler steps."""
+    from oracle.svd_step import OracleStep, dummy_conditioning
+    from vdpp_b200.models import StableVideoUNet
+    oracle, nat = _tiny_pair(None, gemm_impl, attn_impl)
+    ts = StableVideoUNet._default_timestep_schedule(total)
+    model = StableVideoUNet(unet=nat, timesteps=ts).to(DEV)
+    model.use_cuda_graph = graph
+    torch.manual_seed(5)
+    cond = dummy_conditioning(B, Fr, H, W, torch.device(DEV), torch.float16, guidance_scale=cfg_scale)
+    model.set_conditioning(cond.image_embeddings, cond.image_latents, guidance_scale=cfg_scale, num_frames=Fr)
+    ostep = OracleStep(oracle, total)
+    torch.manual_seed(42)
+    x0 = torch.randn(B, 4, Fr, H, W, device=DEV).half() * model.init_noise_sigma
+    a, b = x0.clone(), x0.clone()
+    worst = 0.0
+    rep = 2 if graph else 1
+    for _ in range(rep):          # with graphs: first pass warms + captures, second replays
+        a, b = x0.clone(), x0.clone()
+        for s in range(n_steps):
+            a = model(a, s)
+            b = ostep(b, s, cond)
+    torch.cuda.synchronize()
+    scale = b.float().abs().max().item()
+    r = _cmp(a, b, rel=1e-2, floor=0.0)
+    r["latent_absmax"] = scale
+    return r
+
+
+UNET_CHECKS = {
+    "unet_tiny_simt": lambda: unet_tiny(1, 1),
+    "unet_tiny_tc_gemm": lambda: unet_tiny(0, 1),
+    "unet_tiny_tc": lambda: unet_tiny(0, 0),
+    "unet_tiny_tc_b2": lambda: unet_tiny(0, 0, B=2, Fr=2, H=16, W=32),
+    "svd_steps_simt": lambda: svd_steps(gemm_impl=1, attn_impl=1),
+    "svd_steps_tc": lambda: svd_steps(),
+    "svd_steps_tc_cfg": lambda: svd_steps(cfg_scale=3.0),
+    "svd_steps_tc_graph": lambda: svd_steps(graph=True),
+}

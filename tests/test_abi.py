@@ -1,0 +1,56 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/svdpp.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from vdpp_b200 import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "svdpp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(svdpp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    if not native.library_path().exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(str(native.library_path()))
+    names = _declared()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in svdpp.h but not exported"
+    assert set(names) == set(native.EXPORTED_SYMBOLS)
+
+
+def test_loader_and_error_string():
+    lib = native.load()
+    assert lib.svdpp_abi_version() == 1
+    assert isinstance(lib.svdpp_last_error(), bytes)
+    assert native.groupnorm_workspace_bytes(25, 9216) == (25 * 144 * 32 + 25 * 32) * 8
+
+
+def test_struct_layout_matches_header():
+    # svdpp_gemm_desc / svdpp_attn_desc are passed by pointer: sizes must agree with the C compiler
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "svdpp.h"\nint main(){printf("%zu %zu\\n", sizeof(svdpp_gemm_desc), sizeof(svdpp_attn_desc));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        a, b = map(int, subprocess.check_output([exe]).split())
+    assert a == ctypes.sizeof(native.GemmDesc) and b == ctypes.sizeof(native.AttnDesc)
+
+
+def test_no_cpu_path():
+    import torch
+    with pytest.raises(native.NativeError):
+        native.layernorm(torch.empty(2, 8, dtype=torch.float16), torch.empty(2, 8, dtype=torch.float16),
+                         torch.empty(8, dtype=torch.float16), torch.empty(8, dtype=torch.float16))

@@ -1,0 +1,129 @@
+"""Host-side behaviour of the model adapters (no GPU): API surface, error behaviour, scheduler tables,
+weight-packing arithmetic.  Mirrors what the reference's wrapper promises at src/models/svd_unet.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.scheduler import euler_karras_tables
+from vdpp_b200.models import DummyUNet, StableVideoUNet
+from vdpp_b200.models import scheduler as sched
+from vdpp_b200.models.native_unet import SVD_CONFIG, flops_per_forward, interleave_geglu, window_path_ok
+from vdpp_b200.models.svd_weights import param_count, param_shapes
+from vdpp_b200.native import NativeError
+
+
+class _FakeUNet(torch.nn.Module):
+    def forward(self, **kw):
+        raise AssertionError("must not be reached on CPU")
+
+
+def _wrapper(n=25):
+    return StableVideoUNet(unet=_FakeUNet(), timesteps=StableVideoUNet._default_timestep_schedule(n))
+
+
+@pytest.mark.parametrize("n", [7, 14, 25, 28, 35, 105])
+def test_scheduler_tables_match_oracle(n):
+    sig, ts, ins = euler_karras_tables(n)
+    w = _wrapper(n)
+    assert torch.equal(w.sigmas, sig)
+    assert torch.equal(w.scheduler_timesteps, ts) and w.scheduler_timesteps.device.type == "cpu"
+    assert w.init_noise_sigma == ins
+
+
+def test_step_coefficients_follow_torch_fp32():
+    sig = sched.karras_sigmas(25)
+    for step in (0, 3, 24):
+        in_div, c_v, c_x, s, dt = sched.step_coefficients(sig, step)
+        st = torch.tensor(sig[step])
+        assert in_div == float(((st ** 2 + 1) ** 0.5).half())
+        assert c_v == float(-st / (st ** 2 + 1) ** 0.5)
+        assert c_x == float(st ** 2 + 1)
+        assert dt == float(torch.tensor(float(sig[step + 1]) - float(sig[step]), dtype=torch.float32))
+
+
+def test_default_timestep_schedule():
+    s = StableVideoUNet._default_timestep_schedule(25)
+    assert len(s) == 25 and s[0] == 999 and s[1] == 959 and s[-1] == 39
+    assert len(StableVideoUNet._default_timestep_schedule(28)) == 28
+
+
+def test_wrapper_error_behaviour():
+    w = _wrapper()
+    x = torch.zeros(1, 4, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        w(x, 0)                                   # conditioning not set (svd_unet.py:367-371)
+    w.set_dummy_conditioning(1, 3, 8, 8, torch.device("cpu"))
+    with pytest.raises(ValueError):
+        w(x, 25)                                  # step out of range (svd_unet.py:374-375)
+    with pytest.raises(ValueError):
+        w(x, -1)
+    with pytest.raises(NativeError):
+        w(x, 0)                                   # no CPU path, and it says so
+    w.clear_conditioning()
+    with pytest.raises(RuntimeError):
+        w(x, 0)
+
+
+def test_conditioning_state():
+    w = _wrapper()
+    torch.manual_seed(0)
+    w.set_dummy_conditioning(2, 5, 8, 8, torch.device("cpu"), guidance_scale=3.0)
+    assert w._image_embeddings.shape == (2, 1, 1024) and w._image_embeddings.dtype == torch.float16
+    assert w._image_latents.shape == (2, 4, 5, 8, 8)
+    ids = w._added_time_ids
+    assert ids.shape == (2, 3) and ids.dtype == torch.float16
+    assert ids[0, 0] == 5 and ids[0, 1] == 127 and abs(float(ids[0, 2]) - 0.020004) < 1e-5   # fp16(0.02), Q8
+    assert w._guidance_scale_tensor.shape == (1, 1, 5, 1, 1)
+    assert torch.equal(w._guidance_scale_tensor.flatten().float(), torch.linspace(1, 3, 5).half().float())
+    assert not w._uncond_embeddings.any() and not w._uncond_image_latents.any()
+    w.set_conditioning(torch.randn(1, 1024), torch.randn(1, 4, 5, 8, 8), guidance_scale=1.0, num_frames=5)
+    assert w._image_embeddings.shape == (1, 1, 1024) and w._guidance_scale_tensor is None
+    w.enable_memory_optimizations()               # tolerated no-op
+
+
+def test_param_inventory():
+    assert param_count() == 1_524_623_082
+    shapes = param_shapes()
+    assert shapes["conv_in.weight"] == (320, 8, 3, 3)
+    assert shapes["up_blocks.1.resnets.2.spatial_res_block.conv1.weight"] == (1280, 1920, 3, 3)
+    assert shapes["mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (1280, 1024)
+
+
+def test_geglu_interleave_is_a_permutation_of_chunk_semantics():
+    torch.manual_seed(0)
+    C = 64
+    inner = 4 * C                                  # 256 -> padded to 320 (4 tiles of 80)
+    w, b = torch.randn(2 * inner, C), torch.randn(2 * inner)
+    wi, bi, n = interleave_geglu(w, b)
+    assert n == inner and wi.shape == (640, C) and bi.shape == (640,)
+    x = torch.randn(5, C)
+    y = x @ wi.t() + bi
+    y = y.reshape(5, 4, 2, 80)
+    val, gate = y[:, :, 0].reshape(5, 320)[:, :inner], y[:, :, 1].reshape(5, 320)[:, :inner]
+    ref = x @ w.t() + b
+    torch.testing.assert_close(val, ref[:, :inner])
+    torch.testing.assert_close(gate, ref[:, inner:])
+    assert not wi.reshape(4, 2, 80, C)[3, :, 16:].any()    # padding rows are zero
+
+
+def test_window_path_rule_and_flops():
+    assert all(window_path_ok(w, 320) for w in (128, 64, 32, 16, 8, 256))
+    assert not any(window_path_ok(w, 320) for w in (4, 72, 40, 2))
+    assert not window_path_ok(128, 8)
+    fl25 = flops_per_forward(SVD_CONFIG, 1, 25, 72, 128)
+    fl14 = flops_per_forward(SVD_CONFIG, 1, 14, 72, 128)
+    # 79.946 TFLOP at 25 frames, including work this build never runs: the dead cross-attention q
+    # projections (1.439), the cross-attention out projections on every token (1.439; here a per-image
+    # vector), the k/v projections (0.108) and the embedding MLPs (0.008)
+    assert abs(fl25["total"] / 1e12 - (79.946 - 1.439 - 1.439 - 0.108 - 0.008)) < 0.05
+    assert abs(fl25["attn_spatial"] / 1e12 - 15.503) < 0.01 and abs(fl25["geglu_ff"] / 1e12 - 25.905) < 0.01
+    assert abs(fl14["total"] / fl25["total"] - 14 / 25) < 2e-3
+
+
+def test_dummy_unet_interface():
+    m = DummyUNet(channels=8)
+    assert set(m.state_dict()) == {"net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias", "norm.weight", "norm.bias"}
+    for shape in ((1, 8, 8, 16, 16), (2, 8, 4, 32, 32)):
+        x = torch.randn(*shape)
+        assert m(x, step=10).shape == x.shape
+    assert DummyUNet(channels=4, use_layernorm=False).norm is None

@@ -1,0 +1,166 @@
+"""Stage runner on CPU/gloo (BASELINE config 1): argument validation, single-process run, and the
+world-size invariance property — the final latent is bit-identical (same SHA-256) whether the schedule
+runs on 1, 2 or 4 ranks — including the uneven 25-step split."""
+import hashlib
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vdpp_b200.distributed import finalize_distributed, init_distributed, resolve_backend
+from vdpp_b200.models import DummyUNet
+from vdpp_b200.pipeline import (LatentSpec, PipelineConfig, PipelineStage, run_pipeline_latents, run_single_latent)
+
+SHAPE = (1, 4, 3, 8, 8)
+
+
+def _spec():
+    return LatentSpec(shape=torch.Size(SHAPE), dtype=torch.float32, device=torch.device("cpu"))
+
+
+def _model():
+    torch.manual_seed(1234)          # the reference does not seed (Q4); every rank must, to agree
+    return DummyUNet(channels=4).eval()
+
+
+def _supplier(i):
+    g = torch.Generator().manual_seed(42 + i)
+    return torch.randn(SHAPE, generator=g)
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def test_backend_resolution(monkeypatch):
+    monkeypatch.delenv("PIPELINE_BACKEND", raising=False)
+    assert resolve_backend(None, simulator=True) == "gloo"
+    assert resolve_backend(None) == "nccl"
+    assert resolve_backend("GLOO") == "gloo"
+    monkeypatch.setenv("PIPELINE_BACKEND", "gloo")
+    assert resolve_backend(None) == "gloo"
+    assert resolve_backend("nccl") == "nccl"          # explicit argument wins over the environment
+    with pytest.raises(ValueError):
+        resolve_backend("mpi")
+    monkeypatch.setenv("PIPELINE_BACKEND", "ucc")
+    with pytest.raises(ValueError):
+        resolve_backend(None)
+
+
+def test_config_and_argument_validation():
+    with pytest.raises(ValueError):
+        PipelineConfig(total_steps=4, world_size=1, rank=0, timesteps=[0, 1, 2], latent_spec=_spec())
+    cfg = PipelineConfig(total_steps=4, world_size=1, rank=0, timesteps=[3, 2, 1, 0], latent_spec=_spec())
+    st = PipelineStage(_model(), cfg)
+    assert (st.step_range.start, st.step_range.end) == (0, 4)
+    with pytest.raises(ValueError):
+        st.run(None)                                   # rank 0 needs an input
+    with pytest.raises(ValueError):
+        st.run_many(0, input_supplier=_supplier)
+    with pytest.raises(ValueError):
+        st.run_many(2)                                 # rank 0 needs a supplier
+    with pytest.raises(ValueError):                    # reference rule: 25 steps on 4 ranks is an error ...
+        PipelineStage(_model(), PipelineConfig(25, 4, 0, list(range(25)), _spec()))
+    ok = PipelineStage(_model(), PipelineConfig(25, 4, 0, list(range(25)), _spec(), allow_uneven=True))
+    assert ok.step_range.count == 7                    # ... unless the uneven extension is requested
+    mid = PipelineStage(_model(), PipelineConfig(4, 2, 1, [3, 2, 1, 0], _spec()))
+    with pytest.raises(ValueError):
+        mid._process_single_latent(torch.zeros(SHAPE), 0)   # non-zero ranks must not be handed a latent
+
+
+def test_single_rank_passes_timestep_values_in_order():
+    seen = []
+
+    class Probe(torch.nn.Module):
+        def forward(self, latent, step):
+            seen.append(step)
+            return latent + 1
+
+    ts = [9, 7, 5, 3]
+    out = run_single_latent(Probe(), total_steps=4, timesteps=ts, world_size=1, rank=0, latent_spec=_spec(),
+                            input_latent=torch.zeros(SHAPE))
+    assert seen == ts and torch.equal(out, torch.full(SHAPE, 4.0))       # values, not indices (Q2)
+    outs = run_pipeline_latents(Probe(), total_steps=4, timesteps=ts, world_size=1, rank=0, latent_spec=_spec(),
+                                num_samples=3, input_supplier=lambda i: torch.full(SHAPE, float(i)))
+    assert [o.flatten()[0].item() for o in outs] == [4.0, 5.0, 6.0]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total_steps, n_samples, uneven, use_run_many, q):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    torch.set_num_threads(1)
+    init_distributed(backend="gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    model = _model()
+    ts = list(reversed(range(total_steps)))            # simulator convention (simulator.py:77-79)
+    cfg = PipelineConfig(total_steps, world, rank, ts, _spec(), allow_uneven=uneven)
+    stage = PipelineStage(model, cfg)
+    with torch.no_grad():
+        if use_run_many:
+            outs = stage.run_many(n_samples, input_supplier=_supplier if rank == 0 else None)
+        else:                                           # the reference benchmark's call pattern (benchmark.py:229-235)
+            outs = []
+            for i in range(n_samples):
+                o = stage._process_single_latent(_supplier(i) if rank == 0 else None, sample_idx=i)
+                if o is not None:
+                    outs.append(o)
+            outs = outs or None
+    if rank == world - 1:
+        q.put([_sha(o) for o in outs])
+    else:
+        assert outs is None                             # Q10: only the last rank returns latents
+    dist.barrier()
+    finalize_distributed()
+
+
+def _run_world(world, total_steps, n_samples=3, uneven=False, use_run_many=True):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total_steps, n_samples, uneven, use_run_many, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def _single_process(total_steps, n_samples=3):
+    model = _model()
+    ts = list(reversed(range(total_steps)))
+    out = []
+    with torch.no_grad():
+        for i in range(n_samples):
+            x = _supplier(i)
+            for t in ts:
+                x = model(x, t)
+            out.append(_sha(x))
+    return out
+
+
+@pytest.mark.timeout(300)
+def test_world_size_invariance_even_split():
+    want = _single_process(28)
+    assert _run_world(2, 28) == want
+    assert _run_world(4, 28) == want
+    assert _run_world(4, 28, use_run_many=False) == want
+
+
+@pytest.mark.timeout(300)
+def test_world_size_invariance_uneven_split():
+    want = _single_process(25)
+    assert _run_world(2, 25, uneven=True) == want
+    assert _run_world(4, 25, uneven=True) == want          # stages of 7, 6, 6, 6 steps (BASELINE config 1)

@@ -1,0 +1,100 @@
+"""Full-size parity experiment (BASELINE config 2 by default: 14 frames, 72x128 latent, 25 Euler steps):
+the native path vs the torch oracle run with library kernels in fp16 (= 'the reference's own torch fp16
+pipeline') on the same seeded weights, conditioning and initial noise, plus the library path's own
+run-to-run/backend-to-backend deviation (the noise floor for the 2e-2 / cos>=0.999 tolerance) and, when
+--fp32, the deviation of both from an fp32 run.  Writes gpurun_out/full_parity.json.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.nn.functional as Fn  # noqa: E402
+
+import vdpp_b200  # noqa: E402,F401
+from oracle.svd_step import Conditioning, OracleStep  # noqa: E402
+from oracle.unet_torch import UNetSpatioTemporalConditionModel  # noqa: E402
+from vdpp_b200.models import StableVideoUNet  # noqa: E402
+from vdpp_b200.models.native_unet import NativeUNet  # noqa: E402
+
+
+def diff(a, b):
+    a, b = a.float(), b.float()
+    return dict(max_abs=(a - b).abs().max().item(), mean_abs=(a - b).abs().mean().item(),
+                cos=Fn.cosine_similarity(a.flatten(), b.flatten(), dim=0).item(), ref_absmax=b.abs().max().item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=14)
+    ap.add_argument("--height", type=int, default=72)
+    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--guidance-scale", type=float, default=None)
+    ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--out", default="full_parity.json")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    F_, H, W, T = a.frames, a.height, a.width, a.steps
+    torch.manual_seed(0)
+    with torch.device(dev):
+        lib = UNetSpatioTemporalConditionModel().eval()        # default init from seed 0, on the GPU
+    lib = lib.half()
+    nat = NativeUNet(lib.state_dict(), device=dev)
+    ts = StableVideoUNet._default_timestep_schedule(T)
+    model = StableVideoUNet(unet=nat, timesteps=ts).to(dev)
+    torch.manual_seed(1)
+    emb = torch.randn(1, 1, 1024, device=dev).half()
+    img = torch.randn(1, 4, F_, H, W, device=dev).half()
+    model.set_conditioning(emb, img, guidance_scale=a.guidance_scale, num_frames=F_)
+    cond = Conditioning(emb, img, dtype=torch.float16, guidance_scale=a.guidance_scale, num_frames=F_)
+    torch.manual_seed(42)
+    x0 = (torch.randn(1, 4, F_, H, W, device=dev) * model.init_noise_sigma).half()
+    ostep = OracleStep(lib, T)
+    res = dict(frames=F_, latent=[H, W], steps=T, guidance=a.guidance_scale, per_step=[])
+
+    # first-step UNet output parity (before any trajectory divergence)
+    xa, xb, xc = x0.clone(), x0.clone(), x0.clone()
+    torch.backends.cudnn.benchmark = False
+    t0 = time.time()
+    for s in range(T):
+        xa = model(xa, s)                                   # native
+        xb = ostep(xb, s, cond)                             # library fp16, default backends
+        torch.backends.cudnn.benchmark = True               # library fp16, other conv algos + math SDPA
+        with torch.nn.attention.sdpa_kernel([torch.nn.attention.SDPBackend.EFFICIENT_ATTENTION]):
+            xc = ostep(xc, s, cond)
+        torch.backends.cudnn.benchmark = False
+        if s in (0, 1, 4, 9, 14, 19, T - 1):
+            res["per_step"].append(dict(step=s + 1, native_vs_lib=diff(xa, xb), lib_vs_lib2=diff(xc, xb)))
+            print(json.dumps(res["per_step"][-1]), flush=True)
+    torch.cuda.synchronize()
+    res["secs"] = time.time() - t0
+    res["final_native_vs_lib"] = diff(xa, xb)
+    res["final_lib_vs_lib2"] = diff(xc, xb)
+    res["finite"] = bool(torch.isfinite(xa).all() and torch.isfinite(xb).all())
+    if a.fp32:
+        del nat, model
+        torch.cuda.empty_cache()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        lib32 = lib.float()   # same fp16-rounded weights, fp32 arithmetic
+        o32 = OracleStep(lib32, T, dtype=torch.float32)
+        c32 = Conditioning(emb.float(), img.float(), dtype=torch.float32, guidance_scale=a.guidance_scale, num_frames=F_)
+        x32 = x0.float()
+        for s in range(T):
+            x32 = o32(x32, s, c32)
+        res["final_native_vs_fp32"] = diff(xa, x32)
+        res["final_lib_vs_fp32"] = diff(xb, x32)
+    tol_ok = res["final_native_vs_lib"]["max_abs"] <= 2e-2 and res["final_native_vs_lib"]["cos"] >= 0.999
+    res["within_north_star_tolerance"] = bool(tol_ok)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", a.out), "w"), indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k != "per_step"}, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -374,9 +374,9 @@ __global__ void euler_vpred_kernel(const __half* __restrict__ latent, const __ha
       __half v = va[vi];
       if (vc != nullptr) {
         // fp16 arithmetic, one rounding per op, as torch does at svd_unet.py:411
-        const __half d = __hsub(vc[vi], v);
-        const __half e = __hmul(gs[f], d);
-        v = __hadd(v, e);
+        const __half d = __hsub_rn(vc[vi], v);   // _rn: no contraction of mul+add into an fma
+        const __half e = __hmul_rn(gs[f], d);
+        v = __hadd_rn(v, e);
       }
       const long long li = ((b * C + c) * F + f) * HW + p;
       const float x = __half2float(latent[li]);

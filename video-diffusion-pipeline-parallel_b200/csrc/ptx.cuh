@@ -55,7 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (launch error, process survives) instead of hanging the box.
 #ifndef SVDPP_SPIN_LIMIT
-#define SVDPP_SPIN_LIMIT (1u << 27)
+#define SVDPP_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t spins = 0;

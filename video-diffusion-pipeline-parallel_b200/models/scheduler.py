@@ -45,12 +45,14 @@ def init_noise_sigma(sigmas: np.ndarray) -> float:
 def step_coefficients(sigmas: np.ndarray, step: int) -> Tuple[float, float, float, float, float]:
     """Host-side scalars of one Euler v-prediction step, in the precisions torch uses at
     svd_unet.py:382,428-437: (in_div, c_v, c_x, sigma, dt) with
-      in_div = sqrt(sigma^2+1)   c_v = -sigma/sqrt(sigma^2+1)   c_x = sigma^2+1   (all float32 ops)
-      dt     = float32(float64(sigma_next) - float64(sigma))."""
+      in_div = fp16(sqrt(sigma^2+1))   c_v = -sigma/sqrt(sigma^2+1)   c_x = sigma^2+1   (float32 ops)
+      dt     = float32(float64(sigma_next) - float64(sigma)).
+    in_div is rounded to fp16 because `latent / sqrt(sigma^2+1)` at :382 divides an fp16 tensor by a
+    0-dim fp32 tensor: torch's result type is fp16 and the 0-dim operand is cast to it first."""
     s = np.float32(sigmas[step])
     s_next = np.float32(sigmas[step + 1])
     c_x = np.float32(s * s + np.float32(1.0))
     root = np.sqrt(c_x, dtype=np.float32)
     c_v = np.float32(-s / root)
     dt = np.float32(float(s_next) - float(s))
-    return float(root), float(c_v), float(c_x), float(s), float(dt)
+    return float(np.float16(root)), float(c_v), float(c_x), float(s), float(dt)

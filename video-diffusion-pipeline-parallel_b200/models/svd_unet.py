@@ -269,10 +269,16 @@ class StableVideoUNet(nn.Module):
             graph = torch.cuda.CUDAGraph()
             if self._graph_pool is None:
                 self._graph_pool = torch.cuda.graph_pool_handle()
+            from .. import native
+            before = native.LAUNCHES
             with torch.cuda.graph(graph, pool=self._graph_pool):
                 g_out = self._step(g_in, step)
-            self._graphs[key] = (graph, g_in, g_out)
-        graph, g_in, g_out = self._graphs[key]
+            n_kernels = native.LAUNCHES - before
+            native.LAUNCHES = before          # capture launches nothing; replays are counted below
+            self._graphs[key] = (graph, g_in, g_out, n_kernels)
+        graph, g_in, g_out, n_kernels = self._graphs[key]
         g_in.copy_(latent)
         graph.replay()
+        from .. import native
+        native.LAUNCHES += n_kernels
         return g_out.clone()

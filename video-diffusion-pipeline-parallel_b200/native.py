@@ -64,6 +64,16 @@ class AttnDesc(C.Structure):
 
 _lib = None
 
+# Number of libsvdpp kernels launched through this binding (bench.py reports it as gpu_launches).
+LAUNCHES = 0
+# Optional profiling hook: when set to a list, gemm()/attn_spatial() append (kind, flops, start_evt, end_evt).
+PROFILE = None
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def library_path() -> pathlib.Path:
     return _LIB_PATH
@@ -199,7 +209,15 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
     d.geglu = 1 if geglu else 0
     d.D, d.ldd = out.data_ptr(), out.stride(0)
     d.n_store = n_store
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _check(lib.svdpp_gemm_f16(C.byref(d), impl, _stream()), "svdpp_gemm_f16")
+    if PROFILE is not None:
+        e1.record()
+        kind = "conv" if conv_dims is not None else ("geglu" if geglu else "linear")
+        PROFILE.append((kind, 2.0 * d.M * N * K, (d.M, N, K), e0, e1))
+    _count()
     return out
 
 
@@ -211,7 +229,14 @@ def attn_spatial(out: torch.Tensor, qkv: torch.Tensor, *, n_img: int, S: int, he
     d.q_off, d.k_off, d.v_off = q_off, k_off, v_off
     d.out, d.ldo = out.data_ptr(), out.stride(0)
     d.n_img, d.S, d.heads, d.scale = n_img, S, heads, scale
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _check(load().svdpp_attn_spatial_f16(C.byref(d), impl, _stream()), "svdpp_attn_spatial_f16")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("attn_spatial", 4.0 * S * S * 64 * heads * n_img, (n_img, S, heads), e0, e1))
+    _count()
     return out
 
 
@@ -221,6 +246,7 @@ def attn_temporal(out: torch.Tensor, qkv: torch.Tensor, *, B: int, F: int, HW: i
     _check(load().svdpp_attn_temporal_f16(qkv.data_ptr(), qkv.stride(0), q_off, k_off, v_off, out.data_ptr(),
                                           out.stride(0), B, F, HW, heads, scale, _stream()),
            "svdpp_attn_temporal_f16")
+    _count(1)
     return out
 
 
@@ -237,6 +263,7 @@ def groupnorm_silu(out, x1, gamma, beta, *, n_img, HW, eps, silu=True, x2=None, 
                                        out.data_ptr(), n_img, HW, frames_per_stat, eps, 1 if silu else 0,
                                        workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                        _stream()), "svdpp_groupnorm_silu")
+    _count(3)
     return out
 
 
@@ -246,6 +273,7 @@ def layernorm(out, x, gamma, beta, *, eps=1e-5, addvec=None, add_hw=1, add_mod=1
     _check(load().svdpp_layernorm(x.data_ptr(), x.stride(0), _ptr(addvec), add_hw, add_mod, gamma.data_ptr(),
                                   beta.data_ptr(), out.data_ptr(), out.stride(0), M, Cc, eps, _stream()),
            "svdpp_layernorm")
+    _count(1)
     return out
 
 
@@ -258,6 +286,7 @@ def linear_small(out, x, w, bias=None, *, x_add=None, act_in=0, act_out=0) -> to
     _check(load().svdpp_linear_small(x.data_ptr(), _ptr(x_add), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
                                      out.data_ptr(), out.stride(0), R, N, K, act_in, act_out, _stream()),
            "svdpp_linear_small")
+    _count(1)
     return out
 
 
@@ -273,6 +302,7 @@ def sinusoid_embed(out, src: Optional[torch.Tensor], *, n_vals: int, dim: int, s
         raise NativeError("sinusoid_embed: src must be fp32 or fp16")
     _check(load().svdpp_sinusoid_embed(_ptr(src), kind, src_mod, n_vals, dim, out.data_ptr(), _stream()),
            "svdpp_sinusoid_embed")
+    _count(1)
     return out
 
 
@@ -280,6 +310,7 @@ def upsample2x(out, x, *, n_img, H, W, Cc) -> torch.Tensor:
     _req(out), _req(x)
     _check(load().svdpp_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), n_img, H, W, Cc, _stream()),
            "svdpp_upsample2x_nhwc")
+    _count(1)
     return out
 
 
@@ -290,6 +321,7 @@ def im2col(out, x, *, B, F, H, W, Cc, Ho, Wo, stride, taps) -> torch.Tensor:
         arr[4 * i], arr[4 * i + 1], arr[4 * i + 2], arr[4 * i + 3] = dw, dh, df, 0
     _check(load().svdpp_im2col_nhwc(x.data_ptr(), out.data_ptr(), out.stride(0), B, F, H, W, Cc, Ho, Wo, stride,
                                     len(taps), C.cast(arr, C.c_void_p), _stream()), "svdpp_im2col_nhwc")
+    _count(1)
     return out
 
 
@@ -300,6 +332,7 @@ def pack_unet_input(out, src0, strides0, C0, in_div, src1, strides1, C1, *, B, F
     _check(load().svdpp_pack_unet_input(src0.data_ptr(), strides0[0], strides0[1], strides0[2], C0, in_div,
                                         _ptr(src1), s1[0], s1[1], s1[2], C1, out.data_ptr(),
                                         1 if out_bfchw else 0, B, F, H, W, _stream()), "svdpp_pack_unet_input")
+    _count(1)
     return out
 
 
@@ -307,6 +340,7 @@ def nhwc_to_bfchw(out, x, *, B, F, Cc, H, W) -> torch.Tensor:
     _req(out), _req(x)
     _check(load().svdpp_nhwc_to_bfchw(x.data_ptr(), out.data_ptr(), B, F, Cc, H, W, _stream()),
            "svdpp_nhwc_to_bfchw")
+    _count(1)
     return out
 
 
@@ -317,6 +351,7 @@ def euler_vpred_step(out, latent, v_a, *, v_cond=None, gs=None, v_nhwc: bool, c_
     _check(load().svdpp_euler_vpred_step(latent.data_ptr(), v_a.data_ptr(), _ptr(v_cond), _ptr(gs),
                                          1 if v_nhwc else 0, c_v, c_x, sigma, dt, out.data_ptr(), B, Cc, F, H, W,
                                          _stream()), "svdpp_euler_vpred_step")
+    _count(1)
     return out
 
 
@@ -328,4 +363,5 @@ def dummy_unet_step(out, x, w1, b1, w2, b2, ln_g, ln_b, ln_eps, tanh_scale, hidd
     _check(load().svdpp_dummy_unet_step(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                         _ptr(ln_g), _ptr(ln_b), ln_eps, tanh_scale, hidden_ws.data_ptr(),
                                         out.data_ptr(), B, Cc, Ch, F, H, W, _stream()), "svdpp_dummy_unet_step")
+    _count(3)
     return out
