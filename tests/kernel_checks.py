@@ -110,9 +110,17 @@ def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
 
 
 # ------------------------------------------------------------------------------------------ attention
-def attn_spatial(n_img=2, S=320, heads=2, impl=0):
+def attn_spatial(n_img=2, S=320, heads=2, impl=0, growing=False):
     C = heads * 64
     qkv = _rand(n_img * S, 3 * C, seed=1)
+    if growing:
+        # keys grow along the sequence so later key blocks raise the row maximum by far more than 2^8:
+        # exercises the lazy O-rescale path of the tcgen05 kernel
+        ramp = (1.0 + 6.0 * (torch.arange(n_img * S, device=DEV) % S).float() / S)[:, None]
+        qkv = qkv.float()
+        qkv[:, :C] *= 2.0
+        qkv[:, C:2 * C] *= ramp
+        qkv = qkv.half()
     out = torch.full((n_img * S, C), float("nan"), device=DEV, dtype=torch.float16)
     native.attn_spatial(out, qkv, n_img=n_img, S=S, heads=heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125,
                         impl=impl)
@@ -313,6 +321,8 @@ ALL_CHECKS = {
     "tc_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=0),
     "tc_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=0),
     "tc_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=0),
+    "tc_attn_spatial_rescale": lambda: attn_spatial(n_img=2, S=1000, heads=2, impl=0, growing=True),
+    "simt_attn_spatial_rescale": lambda: attn_spatial(n_img=1, S=600, heads=1, impl=1, growing=True),
 }
 
 

@@ -32,117 +32,126 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
+// Thread mapping shared by the statistics and the apply kernel: blockDim = (C/8, rows); thread (tx, ty)
+// owns the 8 channels [8*tx, 8*tx+8) and walks the pixels ty, ty+rows, ... of a 64-pixel chunk, so
+// consecutive threads touch consecutive 16-byte vectors (also across pixel boundaries) and per-channel
+// quantities (running sums, or scale/shift) live in registers.  grid = (chunks, images).
 constexpr int GN_PIX_PER_CHUNK = 64;
 constexpr int GN_GROUPS = 32;
-constexpr int GN_MAX_PAIRS_PER_THREAD = 6;  // 256 threads * 6 pairs * 2 = 3072 channels max
+
+__device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const __half* x2, int C2, long long pix,
+                                                int c0) {
+  return c0 < C1 ? x1 + pix * C1 + c0 : x2 + pix * C2 + (c0 - C1);
+}
 
 // partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
                   float2* __restrict__ partial) {
-  extern __shared__ float2 pair_sums[];  // [C/2]
+  extern __shared__ float2 red[];  // [rows][C]
   const int C = C1 + C2;
-  const int npairs = C >> 1;
+  const int rows = blockDim.y;
+  const int c0 = threadIdx.x * 8;
   const int n = blockIdx.y;
-  const int chunk = blockIdx.x;
-  const int p0 = chunk * GN_PIX_PER_CHUNK;
+  const int p0 = blockIdx.x * GN_PIX_PER_CHUNK;
   const int p1 = min(p0 + GN_PIX_PER_CHUNK, HW);
-  float s[GN_MAX_PAIRS_PER_THREAD], ss[GN_MAX_PAIRS_PER_THREAD];
-  const __half* base[GN_MAX_PAIRS_PER_THREAD];
-  int pitch[GN_MAX_PAIRS_PER_THREAD];
+  float s[8], ss[8];
 #pragma unroll
-  for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
-    s[k] = 0.f;
-    ss[k] = 0.f;
-    const int cp = threadIdx.x + k * 256;
-    const int c = 2 * cp;
-    if (cp < npairs) {
-      if (c < C1) {
-        base[k] = x1 + static_cast<long long>(n) * HW * C1 + c;
-        pitch[k] = C1;
-      } else {
-        base[k] = x2 + static_cast<long long>(n) * HW * C2 + (c - C1);
-        pitch[k] = C2;
-      }
-    } else {
-      base[k] = nullptr;
-      pitch[k] = 0;
-    }
-  }
-  for (int p = p0; p < p1; ++p) {
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  for (int p = p0 + threadIdx.y; p < p1; p += rows) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, static_cast<long long>(n) * HW + p, c0)), v);
 #pragma unroll
-    for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
-      if (base[k] != nullptr) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(base[k] + static_cast<long long>(p) * pitch[k]));
-        s[k] += f.x + f.y;
-        ss[k] += f.x * f.x + f.y * f.y;
-      }
+    for (int j = 0; j < 8; ++j) {
+      s[j] += v[j];
+      ss[j] += v[j] * v[j];
     }
   }
 #pragma unroll
-  for (int k = 0; k < GN_MAX_PAIRS_PER_THREAD; ++k) {
-    const int cp = threadIdx.x + k * 256;
-    if (cp < npairs) pair_sums[cp] = make_float2(s[k], ss[k]);
-  }
+  for (int j = 0; j < 8; ++j) red[threadIdx.y * C + c0 + j] = make_float2(s[j], ss[j]);
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    const int ppg = npairs / GN_GROUPS;  // pairs per group
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < GN_GROUPS) {
+    const int cpg = C / GN_GROUPS;
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < ppg; ++i) {
-      const float2 v = pair_sums[threadIdx.x * ppg + i];
-      a += v.x;
-      b += v.y;
-    }
-    partial[(static_cast<long long>(n) * gridDim.x + chunk) * GN_GROUPS + threadIdx.x] = make_float2(a, b);
+    for (int r = 0; r < rows; ++r)
+      for (int i = 0; i < cpg; ++i) {
+        const float2 v = red[r * C + tid * cpg + i];
+        a += v.x;
+        b += v.y;
+      }
+    partial[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS + tid] = make_float2(a, b);
   }
 }
 
-// stats[st][g] = (mean, rstd), st = image / frames_per_stat
-__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int n_chunks, int frames_per_stat,
-                                   float count, float eps, float2* __restrict__ stats) {
-  const int st = blockIdx.x;
-  const int g = threadIdx.x;
-  if (g >= GN_GROUPS) return;
-  double a = 0.0, b = 0.0;
-  for (int f = 0; f < frames_per_stat; ++f) {
-    const long long n = static_cast<long long>(st) * frames_per_stat + f;
-    for (int c = 0; c < n_chunks; ++c) {
-      const float2 v = partial[(n * n_chunks + c) * GN_GROUPS + g];
-      a += v.x;
-      b += v.y;
-    }
-  }
-  const double mean = a / count;
-  double var = b / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[st * GN_GROUPS + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-}
-
+// stats[st][g] = (mean, rstd), st = image / frames_per_stat; 8 threads per group, fixed summation order
 __global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float2* __restrict__ partial, int n_chunks, int frames_per_stat, float count, float eps,
+                   float2* __restrict__ stats) {
+  __shared__ double sa[GN_GROUPS][8], sb[GN_GROUPS][8];
+  const int st = blockIdx.x;
+  const int g = threadIdx.x & 31;
+  const int part = threadIdx.x >> 5;
+  const int total = frames_per_stat * n_chunks;
+  const float2* base = partial + static_cast<long long>(st) * total * GN_GROUPS + g;
+  double a = 0.0, b = 0.0;
+  for (int i = part; i < total; i += 8) {
+    const float2 v = base[static_cast<long long>(i) * GN_GROUPS];
+    a += v.x;
+    b += v.y;
+  }
+  sa[g][part] = a;
+  sb[g][part] = b;
+  __syncthreads();
+  if (part == 0) {
+    a = 0.0;
+    b = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      a += sa[g][i];
+      b += sb[g][i];
+    }
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[st * GN_GROUPS + g] = make_float2(static_cast<float>(mean),
+                                            static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+}
+
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, const float2* __restrict__ stats,
-                __half* __restrict__ out, long long n_vec, int HW, int frames_per_stat, int silu) {
+                __half* __restrict__ out, int HW, int frames_per_stat, int silu) {
   const int C = C1 + C2;
-  const int vpr = C >> 3;  // 8-channel vectors per row
+  const int rows = blockDim.y;
+  const int c0 = threadIdx.x * 8;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * GN_PIX_PER_CHUNK;
+  const int p1 = min(p0 + GN_PIX_PER_CHUNK, HW);
   const int cpg = C / GN_GROUPS;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n_vec;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = idx / vpr;
-    const int c0 = static_cast<int>(idx - m * vpr) << 3;
-    const int st = static_cast<int>(m / HW) / frames_per_stat;
-    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1 + m * C1 + c0)
-                              : *reinterpret_cast<const uint4*>(x2 + m * C2 + (c0 - C1));
-    float v[8], g[8], b[8];
-    unpack8(u, v);
+  const float2* st = stats + (n / frames_per_stat) * GN_GROUPS;
+  float sc[8], sh[8];
+  {
+    float g[8], b[8];
     unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
     unpack8(*reinterpret_cast<const uint4*>(beta + c0), b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 mr = stats[st * GN_GROUPS + (c0 + j) / cpg];
-      float y = (v[j] - mr.x) * mr.y * g[j] + b[j];
+      const float2 mr = st[(c0 + j) / cpg];
+      sc[j] = mr.y * g[j];
+      sh[j] = b[j] - mr.x * sc[j];
+    }
+  }
+  for (int p = p0 + threadIdx.y; p < p1; p += rows) {
+    const long long pix = static_cast<long long>(n) * HW + p;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, pix, c0)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = fmaf(v[j], sc[j], sh[j]);
       v[j] = silu ? silu_f(y) : y;
     }
-    *reinterpret_cast<uint4*>(out + m * C + c0) = pack8(v);
+    *reinterpret_cast<uint4*>(out + pix * C + c0) = pack8(v);
   }
 }
 
@@ -209,6 +218,7 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, const __half* __re
 }
 
 // ------------------------------------------------------------------------------------ small linear
+// One warp per output feature, 16-byte loads along K, up to 8 rows at a time.
 __global__ void __launch_bounds__(128)
 linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ x_add, long long ldx,
                     const __half* __restrict__ W, long long ldw,
@@ -222,22 +232,26 @@ linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ x_a
     float acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    for (int k2 = lane; k2 < (K >> 1); k2 += 32) {
-      const float2 w = __half22float2(*reinterpret_cast<const __half2*>(wr + 2 * k2));
+    for (int k8 = lane; k8 < (K >> 3); k8 += 32) {
+      float w[8];
+      unpack8(*reinterpret_cast<const uint4*>(wr + 8 * k8), w);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r0 + r < R) {
-          float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + static_cast<long long>(r0 + r) * ldx + 2 * k2));
+          float a[8];
+          unpack8(*reinterpret_cast<const uint4*>(x + static_cast<long long>(r0 + r) * ldx + 8 * k8), a);
           if (x_add != nullptr) {
-            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(x_add + static_cast<long long>(r0 + r) * ldx + 2 * k2));
-            a.x = __half2float(__float2half_rn(a.x + a2.x));  // fp16 add, as torch
-            a.y = __half2float(__float2half_rn(a.y + a2.y));
+            float a2[8];
+            unpack8(*reinterpret_cast<const uint4*>(x_add + static_cast<long long>(r0 + r) * ldx + 8 * k8), a2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __half2float(__float2half_rn(a[j] + a2[j]));  // fp16 add, as torch
           }
           if (act_in == 1) {
-            a.x = __half2float(__float2half_rn(silu_f(a.x)));
-            a.y = __half2float(__float2half_rn(silu_f(a.y)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __half2float(__float2half_rn(silu_f(a[j])));
           }
-          acc[r] += a.x * w.x + a.y * w.y;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r] = fmaf(a[j], w[j], acc[r]);
         }
       }
     }
@@ -475,28 +489,36 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   if (x2 == nullptr) C2 = 0;
   const int C = C1 + C2;
   SVDPP_CHECK_ARG(x1 && gamma && beta && out && workspace, "groupnorm: null pointer");
-  SVDPP_CHECK_ARG(C % (2 * GN_GROUPS) == 0 && C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
-  SVDPP_CHECK_ARG(C / 2 <= 256 * GN_MAX_PAIRS_PER_THREAD, "groupnorm: C=%d too large", C);
+  SVDPP_CHECK_ARG(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
+  SVDPP_CHECK_ARG(C / 8 <= 512, "groupnorm: C=%d too large", C);
   SVDPP_CHECK_ARG(frames_per_stat >= 1 && n_img % frames_per_stat == 0, "groupnorm: frames_per_stat=%d", frames_per_stat);
   SVDPP_CHECK_ARG(workspace_bytes >= svdpp_groupnorm_workspace_bytes(n_img, HW), "groupnorm: workspace too small");
   const int n_chunks = (HW + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
   float2* partial = static_cast<float2*>(workspace);
   float2* stats = partial + static_cast<size_t>(n_img) * n_chunks * GN_GROUPS;
-  dim3 g1(n_chunks, n_img);
-  gn_partial_kernel<<<g1, 256, (C / 2) * sizeof(float2), stream>>>(static_cast<const __half*>(x1), C1,
-                                                                   static_cast<const __half*>(x2), C2, HW, partial);
+  const int nvc = C / 8;
+  int rows = 256 / nvc;
+  if (rows < 1) rows = 1;
+  if (rows > GN_PIX_PER_CHUNK) rows = GN_PIX_PER_CHUNK;
+  dim3 block(nvc, rows);
+  dim3 grid(n_chunks, n_img);
+  const size_t red_bytes = static_cast<size_t>(rows) * C * sizeof(float2);
+  static bool configured = false;
+  if (!configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  SVDPP_CHECK_ARG(red_bytes <= 64 * 1024, "groupnorm: reduction buffer too large");
+  gn_partial_kernel<<<grid, block, red_bytes, stream>>>(static_cast<const __half*>(x1), C1,
+                                                        static_cast<const __half*>(x2), C2, HW, partial);
   if (int e = check_launch("gn_partial_kernel")) return e;
   const int n_stats = n_img / frames_per_stat;
   const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
-  gn_finalize_kernel<<<n_stats, 32, 0, stream>>>(partial, n_chunks, frames_per_stat, count, eps, stats);
+  gn_finalize_kernel<<<n_stats, 256, 0, stream>>>(partial, n_chunks, frames_per_stat, count, eps, stats);
   if (int e = check_launch("gn_finalize_kernel")) return e;
-  const long long n_vec = static_cast<long long>(n_img) * HW * (C / 8);
-  gn_apply_kernel<<<grid_for(n_vec, 256), 256, 0, stream>>>(static_cast<const __half*>(x1), C1,
-                                                            static_cast<const __half*>(x2), C2,
-                                                            static_cast<const __half*>(gamma),
-                                                            static_cast<const __half*>(beta), stats,
-                                                            static_cast<__half*>(out), n_vec, HW, frames_per_stat,
-                                                            apply_silu);
+  gn_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
+                                              static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                                              stats, static_cast<__half*>(out), HW, frames_per_stat, apply_silu);
   return check_launch("gn_apply_kernel");
 }
 
@@ -521,7 +543,7 @@ extern "C" int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx,
                                   svdpp_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SVDPP_CHECK_ARG(x && W && y, "linear_small: null pointer");
-  SVDPP_CHECK_ARG(K % 2 == 0 && ldx % 2 == 0 && ldw % 2 == 0, "linear_small: K and pitches must be even");
+  SVDPP_CHECK_ARG(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "linear_small: K and pitches must be multiples of 8");
   SVDPP_CHECK_ARG(R >= 1 && N >= 1, "linear_small: bad shape");
   linear_small_kernel<<<(N + 3) / 4, 128, 0, stream>>>(static_cast<const __half*>(x),
                                                        static_cast<const __half*>(x_add), ldx,

@@ -2,7 +2,8 @@
 //
 // svdpp_attn_spatial_f16 (tcgen05): one CTA per (128-query tile, head, image); 2 CTAs per SM.
 //   warps 0..3  softmax: thread = query row; S row read from TMEM, online softmax in the log2
-//               domain, P written as fp16 into 128B-swizzled smem, O kept in registers
+//               domain, P written as fp16 into 128B-swizzled smem; O accumulates in TMEM and is
+//               rescaled lazily (only when the row maximum grows by more than 2^8)
 //   warp 4      TMA producer: Q once, then K_j / V_j blocks of 128 keys through 2-slot rings
 //   warp 5      TMEM allocator + MMA issuer: S = Q K_j^T (N=128) and O_j = P_j V_j (N=64, V read
 //               MN-major straight from its row-major tile) into TMEM
@@ -128,7 +129,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t da = make_smem_desc_sw128(p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 1024, 0);
           const uint64_t db = make_smem_desc_sw128(v_addr + kk * 2048, 1024, 8192);
-          umma_f16(tmem_O, da, db, idesc_o, kk != 0 ? 1u : 0u);
+          umma_f16(tmem_O, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM
         }
         umma_commit(&v_empty[s]);
         umma_commit(pv_done);
@@ -139,14 +140,14 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
     // ------------------------------------------------------------------ softmax (warps 0..3)
     const int r = threadIdx.x;  // query row in tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -CUDART_INF_F;
+    // O stays in TMEM and is accumulated by the MMAs.  The softmax reference maximum m_used is only
+    // raised when a block's row maximum exceeds it by more than 2^8 (log2 domain), so probabilities
+    // stay <= 256 (exact in fp16/fp32) and the O row needs rescaling only on those rare raises.
+    float m_used = -CUDART_INF_F;
     float l_run = 0.f;
     for (int j = 0; j < p.n_kv; ++j) {
-      const int kv0 = j * 128;
-      const int valid = p.S - kv0;  // keys [0, valid) of this block are real
+      const int valid = p.S - j * 128;  // keys [0, valid) of this block are real
+      const bool tail = valid < 128;    // warp-uniform: only the last key block of an image can be partial
       mbar_wait(s_full, j & 1, 17);
       tc_fence_after();
       // pass 1: row maximum
@@ -156,44 +157,59 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         uint32_t v[32];
         tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
         tmem_ld_wait();
+        if (tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (c * 32 + i >= valid) s = -CUDART_INF_F;
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) v[i] = 0xff800000u;  // -inf
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmax3(mx, __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
-      m_run = m_new;
+      const float m_blk = mx * p.scale_log2;
+      bool raise = false;
+      if (j == 0)
+        m_used = m_blk;
+      else
+        raise = m_blk > m_used + 8.0f;
       if (j > 0) {
-        // fold in O_{j-1} = P_{j-1} V_{j-1}; this also orders our P write after that MMA's P read
+        // P_{j-1} V_{j-1} must have retired before P is overwritten (and before O is touched)
         mbar_wait(pv_done, (j - 1) & 1, 18);
         tc_fence_after();
+        if (__any_sync(0xffffffffu, raise)) {
+          const float m_new = raise ? m_blk : m_used;
+          const float alpha = exp2f(m_used - m_new);
+          m_used = m_new;
+          l_run *= alpha;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
-          tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_x32(tmem_O + lane_sel + c * 32, v);
+          }
+          tmem_st_wait();
         }
       }
-      l_run *= alpha;
       // pass 2: probabilities -> fp16 -> swizzled smem
       float lsum = 0.f;
+      const float neg_m = -m_used;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
         tmem_ld_wait();
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
+        }
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m_new);
-          float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_new);
-          if (c * 32 + 2 * i >= valid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
+          const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
           lsum += p0 + p1;
           __half2 h = __floats2half2_rn(p0, p1);
           packed[i] = *reinterpret_cast<uint32_t*>(&h);
@@ -225,9 +241,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = (o[c * 32 + 2 * i] + __uint_as_float(v[2 * i])) * inv_l;
-          float b = (o[c * 32 + 2 * i + 1] + __uint_as_float(v[2 * i + 1])) * inv_l;
-          __half2 h = __floats2half2_rn(a, b);
+          __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
           packed[i] = *reinterpret_cast<uint32_t*>(&h);
         }
 #pragma unroll

@@ -4,7 +4,9 @@
 //   warp 0      TMA producer   global -> 128B-swizzled smem ring (A tile 128x64, B tile BNx64)
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages)
-//   warps 4..7  epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16 stores
+//   warps 4..11 epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16, staged
+//               through padded smem so residual loads and output stores are fully coalesced;
+//               two warps per TMEM lane quarter, each taking every other column chunk
 // The two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Convolutions never materialise im2col: for tap (dw,dh,df) the producer loads the activation
 // window shifted by the tap through a 5-D tensor map [C, W, H, F, B]; TMA zero-fills the halo.
@@ -37,7 +39,20 @@ struct GemmParams {
   int m_tiles, n_tiles;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational form of erfc (|error| < 1.5e-7,
+// far below the fp16 rounding that follows): 2 MUFU + ~12 FMA-pipe instructions and no branches, about a
+// third of erff()'s cost, which otherwise makes the GEGLU epilogue slower than its K=320 main loop.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * exp2f(z * z * -1.4426950408889634f);  // 0.5*erfc(|x|/sqrt2)
+  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return x * phi;
+}
 
 // torch fp16 semantics of GEGLU: proj output rounded to fp16, gelu(gate) rounded, product rounded
 __device__ __forceinline__ __half geglu_fp16(float val, float gate) {
@@ -67,17 +82,22 @@ struct GemmCfg {
   static constexpr int STAGES = (BN <= 160) ? 5 : 4;
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
   static constexpr int NOUT = GEGLU ? BN / 2 : BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging tile [128][NOUT + 8] fp16: the 16-byte pad makes a quarter-warp's 16-byte row
+  // accesses (row pitch 336 B / 176 B) hit 32 distinct banks
+  static constexpr int C_PITCH = NOUT + 8;
+  static constexpr int C_BYTES = BM * C_PITCH * 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool GEGLU>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, GEGLU>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  __half* sC = reinterpret_cast<__half*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::C_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -99,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 256);
     }
     fence_mbar_init();
   }
@@ -114,42 +134,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * Cfg::BM;
-        const int n0 = (tile % p.n_tiles) * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+    // Lane 0 owns the ring (waits, expect_tx, the B tile); in conv mode lane r < nrows issues the
+    // window box of image row r, whose coordinates are computed once per tile.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * Cfg::BM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      int cw = 0, ch = 0, cf = 0, cb = 0;
+      if (p.conv && lane < p.nrows) {
+        const int px = m0 + lane * p.bw;
+        cw = px % p.cW;
+        const int row = px / p.cW;
+        ch = row % p.cH;
+        const int img = row / p.cH;
+        cf = img % p.cF;
+        cb = img / p.cF;
+      }
+      int tap = 0, kc = 0;  // k-block = (tap, kc)
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          tma_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
           if (!p.conv) {
             if (kb < p.kb_split)
               tma_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
             else
               tma_load_2d(sa, &tmA2, &full[stage], (kb - p.kb_split) * 64, m0);
-          } else {
-            const int tap = kb / p.cpk;
-            const int c0 = (kb - tap * p.cpk) * 64;
-            const int dw = p.taps[tap][0], dh = p.taps[tap][1], df = p.taps[tap][2];
-            for (int r = 0; r < p.nrows; ++r) {
-              const int px = m0 + r * p.bw;
-              const int w = px % p.cW;
-              const int row = px / p.cW;
-              const int h = row % p.cH;
-              const int img = row / p.cH;
-              const int f = img % p.cF;
-              const int b = img / p.cF;
-              tma_load_5d(sa + r * p.bw * 128, &tmA, &full[stage], c0, w + dw, h + dh, f + df, b);
-            }
           }
-          tma_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
-          if (++stage == Cfg::STAGES) {
-            stage = 0;
-            phase ^= 1;
+        }
+        __syncwarp();
+        if (p.conv) {
+          if (lane < p.nrows)
+            tma_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
+                        ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+          if (++kc == p.cpk) {
+            kc = 0;
+            ++tap;
           }
+        }
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -189,15 +218,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int we = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // Per tile: (1) coalesced copy of the R1 residual tile into the staging buffer, (2) accumulator
+    // rows from TMEM, epilogue math, fp16 result back into the staging buffer (TMEM stage released
+    // here), (3) coalesced copy of the staging buffer to global.  Thread = accumulator row.
+    const int we = warp & 3;          // the TMEM lane quarter this warp may read (warp % 4)
+    const int half = (warp - 4) >> 2;  // 0: even column chunks, 1: odd column chunks
     const int row = we * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..255
+    constexpr int VPR = Cfg::NOUT / 8;  // 16-byte vectors per staged row
+    constexpr int CW = GEGLU ? 8 : 16;  // columns per chunk: 10 chunks either way, 5 per warp
+    auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile % p.n_tiles;
-      const int m = m_tile * Cfg::BM + row;
+      const int m_base = m_tile * Cfg::BM;
+      const int m = m_base + row;
       const bool m_ok = m < p.M;
+      const int nout0 = n_tile * Cfg::NOUT;
+      const bool vec_ok = (p.ldd & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
+      if constexpr (!GEGLU) {
+        if (p.R1 != nullptr) {
+          const bool r_vec = (p.ldr1 & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
+          constexpr int NV = Cfg::BM * VPR / 256;  // vectors per thread (10): all loads in flight at once
+          static_assert(Cfg::BM * VPR % 256 == 0, "staging copy assumes a whole number of vectors per thread");
+          uint4 val[NV];
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int i = et + k * 256;
+            const int r = i / VPR, v = i - r * VPR;
+            val[k] = make_uint4(0, 0, 0, 0);
+            if (m_base + r < p.M) {
+              const __half* src = p.R1 + static_cast<long long>(m_base + r) * p.ldr1 + nout0 + v * 8;
+              if (r_vec) {
+                val[k] = *reinterpret_cast<const uint4*>(src);
+              } else {
+                __half tmp[8];
+                for (int j = 0; j < 8; ++j) tmp[j] = (nout0 + v * 8 + j < p.n_store) ? src[j] : __float2half(0.f);
+                val[k] = *reinterpret_cast<uint4*>(tmp);
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int i = et + k * 256;
+            const int r = i / VPR, v = i - r * VPR;
+            *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
+          }
+          epi_bar();
+        }
+      }
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + as * Cfg::ACC_STRIDE;
@@ -206,91 +277,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
         rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld;
       }
+      __half* srow = sC + row * Cfg::C_PITCH;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::NOUT / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c * 16, v);
-        uint32_t g[16];
-        if constexpr (GEGLU) tmem_ld_x16(taddr + BN / 2 + c * 16, g);
+      for (int c = half; c < Cfg::NOUT / CW; c += 2) {
+        uint32_t v[CW];
+        uint32_t g[CW];
+        if constexpr (GEGLU) {
+          tmem_ld_x8(taddr + c * CW, v);
+          tmem_ld_x8(taddr + BN / 2 + c * CW, g);
+        } else {
+          tmem_ld_x16(taddr + c * CW, v);
+        }
         tmem_ld_wait();
-        const int nw = n_tile * BN + c * 16;           // weight-row index of the value columns
-        const int nout = n_tile * Cfg::NOUT + c * 16;  // output column
-        if (m_ok && nout < p.n_store) {
-          float y[16];
+        const int nw = n_tile * BN + c * CW;  // weight-row index of the value columns
+        const int nout = nout0 + c * CW;      // output column
+        float y[CW];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+          float b8[8];
+#pragma unroll
+          for (int hlf = 0; hlf < CW / 8; ++hlf) {
+            load8(p.bias + nw + hlf * 8, b8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+          }
+        }
+        __half o[CW];
+        if constexpr (GEGLU) {
+          float gt[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) gt[j] = __uint_as_float(g[j]);
           if (p.bias != nullptr) {
             float b8[8];
+            load8(p.bias + nw + BN / 2, b8);
 #pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-              load8(p.bias + nw + hlf * 8, b8);
+            for (int j = 0; j < 8; ++j) gt[j] += b8[j];
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) o[j] = geglu_fp16(y[j], gt[j]);
+        } else {
+          if (rv != nullptr && nout < p.n_store) {
+            float b8[8];
+#pragma unroll
+            for (int hlf = 0; hlf < CW / 8; ++hlf) {
+              load8(rv + nw + hlf * 8, b8);
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
             }
           }
-          __half o[16];
-          if constexpr (GEGLU) {
-            float gt[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
-            if (p.bias != nullptr) {
-              float b8[8];
+          for (int j = 0; j < CW; ++j) y[j] *= p.alpha;
+          if (p.R1 != nullptr) {
+            float b8[8];
 #pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                load8(p.bias + nw + BN / 2 + hlf * 8, b8);
+            for (int hlf = 0; hlf < CW / 8; ++hlf) {
+              load8(srow + c * CW + hlf * 8, b8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) gt[hlf * 8 + j] += b8[j];
-              }
+              for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = geglu_fp16(y[j], gt[j]);
-          } else {
-            if (rv != nullptr) {
-              float b8[8];
-#pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                load8(rv + nw + hlf * 8, b8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] *= p.alpha;
-            if (p.R1 != nullptr) {
-              float b8[8];
-#pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                load8(p.R1 + static_cast<long long>(m) * p.ldr1 + nout + hlf * 8, b8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
-              }
-            }
-            if (p.R2 != nullptr) {
-              float b8[8];
-#pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(y[j]);
           }
-          __half* dst = p.D + static_cast<long long>(m) * p.ldd + nout;
-          if (nout + 16 <= p.n_store && (p.ldd & 7) == 0) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-            const uint4* o4 = reinterpret_cast<const uint4*>(o);
-            d4[0] = o4[0];
-            d4[1] = o4[1];
+          if (p.R2 != nullptr && m_ok && nout < p.n_store) {
+            float b8[8];
+#pragma unroll
+            for (int hlf = 0; hlf < CW / 8; ++hlf) {
+              load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) o[j] = __float2half_rn(y[j]);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(srow + c * CW);
+        const uint4* o4 = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) d4[q] = o4[q];
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);  // accumulator stage free: the next tile's MMAs may start
+      epi_bar();
+      for (int i = et; i < Cfg::BM * VPR; i += 256) {
+        const int r = i / VPR, v = i - r * VPR;
+        if (m_base + r < p.M) {
+          const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
+          __half* dst = p.D + static_cast<long long>(m_base + r) * p.ldd + nout0 + v * 8;
+          if (vec_ok) {
+            *reinterpret_cast<uint4*>(dst) = val;
           } else {
-            for (int j = 0; j < 16; ++j)
-              if (nout + j < p.n_store) dst[j] = o[j];
+            const __half* hv = reinterpret_cast<const __half*>(&val);
+            for (int j = 0; j < 8; ++j)
+              if (nout0 + v * 8 + j < p.n_store) dst[j] = hv[j];
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      epi_bar();  // staging buffer reusable
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -396,7 +477,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
   return check_launch("gemm_tc_kernel");
 }
 
