@@ -266,21 +266,20 @@ def main() -> None:
 
     barrier()
     t0 = time.perf_counter()
-    pending = stage._post_recv() if rank > 0 else None
     for i in range(n_videos):
         if rank == 0:
             lat = supply_from_host(i)
         else:
-            work, buf = pending
+            work, buf = stage._post_recv()
             work.wait()
             lat = buf if stage.step_range.count else buf.clone()
-            pending = stage._post_recv() if i + 1 < n_videos else None
         lat = stage._run_local_steps(lat)
         if last:
             host_out.copy_(lat, non_blocking=True)
             torch.cuda.synchronize()
         else:
             stage._send_latent(lat, blocking=False)
+            stage._drain_send()
     stage._drain_send()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)

@@ -9,7 +9,7 @@
 
 namespace svdpp {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);

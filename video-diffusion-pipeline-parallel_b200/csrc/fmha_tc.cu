@@ -4,8 +4,8 @@
 //   warps 0..3  softmax: thread = query row; S row read from TMEM, online softmax in the log2
 //               domain, P written as fp16 into 128B-swizzled smem; O accumulates in TMEM and is
 //               rescaled lazily (only when the row maximum grows by more than 2^8)
-//   warp 4      TMA producer: Q once, then K_j / V_j blocks of 128 keys through 2-slot rings
-//   warp 5      TMEM allocator + MMA issuer: S = Q K_j^T (N=128) and O_j = P_j V_j (N=64, V read
+//   warp 4      TMA producer: Q once, then K_j / V_j blocks of 64 keys through 4-slot rings
+//   warp 5      TMEM allocator + MMA issuer: S_j = Q K_j^T (double buffered) and O += P_j V_j (V read
 //               MN-major straight from its row-major tile) into TMEM
 // svdpp_attn_temporal_f16: sequences of F <= 32 frames per (pixel, head): one warp each, CUDA cores
 //   (0.1 % of the UNet's FLOPs; bandwidth bound).
@@ -25,26 +25,36 @@ struct AttnParams {
   long long ldo;
 };
 
-constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 fp16
-constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128;
+constexpr int ATT_Q_BYTES = 128 * 64 * 2;   // 128 queries x 64 dims
+constexpr int ATT_KV_BYTES = 64 * 64 * 2;   // 64 keys x 64 dims
+constexpr int ATT_KV_STAGES = 4;
+constexpr int ATT_P_BYTES = 128 * 64 * 2;   // 128 queries x 64 keys (one swizzle atom column)
+constexpr int ATT_BKV = 64;
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 2 * ATT_P_BYTES + 256;
 
+// Pipeline per CTA (key blocks of 64, j = 0..n_kv-1):
+//   MMA thread :  S_0, S_1 | wait P_j -> O += P_j V_j ; S_{j+2} -> S buffer j&1 | ...
+//   softmax    :  wait S_j -> row max -> (rare) rescale O -> wait PV_{j-2} -> P_j = exp2(S_j - m) -> signal
+// S and P are double buffered, so the tensor core computes S_{j+1} and P_{j-1}V_{j-1} while the
+// softmax warps work on block j; two CTAs per SM fill the remaining gaps.
 __global__ void __launch_bounds__(192, 2)
-attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                       const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;      // 2 slots
-  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;  // 2 slots
-  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;  // 2 swizzle atoms (keys 0..63 | 64..127)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint8_t* sK = sQ + ATT_Q_BYTES;
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_KV_BYTES;
+  uint8_t* sP = sV + ATT_KV_STAGES * ATT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_ready = bars + 10;
-  uint64_t* pv_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* k_full = bars + 1;                      // [4]
+  uint64_t* k_empty = k_full + ATT_KV_STAGES;       // [4]
+  uint64_t* v_full = k_empty + ATT_KV_STAGES;       // [4]
+  uint64_t* v_empty = v_full + ATT_KV_STAGES;       // [4]
+  uint64_t* s_full = v_empty + ATT_KV_STAGES;       // [2]
+  uint64_t* p_ready = s_full + 2;                   // [2]
+  uint64_t* pv_done = p_ready + 2;                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -58,17 +68,20 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
     __trap();
   }
   if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ATT_KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(pv_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -79,61 +92,61 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // columns [0,128)
-  const uint32_t tmem_O = tmem_base + 128;  // columns [128,192)
+  const uint32_t tmem_O = tmem_base + 128;  // S buffers: columns [0,64) and [64,128); O: [128,192)
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_2d(sQ, &tmQKV, q_full, p.q_off + head * 64, row_base + q0);
+      mbar_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, p.q_off + head * 64, row_base + q0);
       for (int j = 0; j < p.n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % ATT_KV_STAGES;
+        const uint32_t ph = (j / ATT_KV_STAGES) & 1;
         mbar_wait(&k_empty[s], ph ^ 1, 11);
-        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_2d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], p.k_off + head * 64, row_base + j * 128);
+        mbar_expect_tx(&k_full[s], ATT_KV_BYTES);
+        tma_load_2d(sK + s * ATT_KV_BYTES, &tmKV, &k_full[s], p.k_off + head * 64, row_base + j * ATT_BKV);
         mbar_wait(&v_empty[s], ph ^ 1, 12);
-        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_2d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], p.v_off + head * 64, row_base + j * 128);
+        mbar_expect_tx(&v_full[s], ATT_KV_BYTES);
+        tma_load_2d(sV + s * ATT_KV_BYTES, &tmKV, &v_full[s], p.v_off + head * 64, row_base + j * ATT_BKV);
       }
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, false);
-      constexpr uint32_t idesc_o = make_idesc_f16(64, true);
+      constexpr uint32_t idesc_s = make_idesc_f16(64, false);  // S: N = 64 keys, K-major B
+      constexpr uint32_t idesc_o = make_idesc_f16(64, true);   // O: N = 64 dims, V read MN-major
       const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1, 13);
+      auto issue_s = [&](int jj) {
+        const int s = jj % ATT_KV_STAGES;
+        mbar_wait(&k_full[s], (jj / ATT_KV_STAGES) & 1, 13);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + s * ATT_KV_BYTES);
+        const uint32_t d_s = tmem_base + (jj & 1) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_S, make_smem_desc_sw128(q_addr + k * 32, 1024, 0),
-                   make_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(d_s, make_smem_desc_sw128(q_addr + k * 32, 1024, 0), make_smem_desc_sw128(k_addr + k * 32, 1024, 0),
+                   idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&k_empty[s]);
-        umma_commit(s_full);
+        umma_commit(&s_full[jj & 1]);
       };
       mbar_wait(q_full, 0, 14);
       issue_s(0);
+      if (p.n_kv > 1) issue_s(1);
       for (int j = 0; j < p.n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(p_ready, j & 1, 15);  // P_j in smem, S_j fully consumed
-        mbar_wait(&v_full[s], (j >> 1) & 1, 16);
+        const int b = j & 1;
+        const int s = j % ATT_KV_STAGES;
+        mbar_wait(&p_ready[b], (j >> 1) & 1, 15);  // P_j in smem, S_j fully consumed
+        mbar_wait(&v_full[s], (j / ATT_KV_STAGES) & 1, 16);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + s * ATT_TILE_BYTES);
+        const uint32_t p_addr = smem_u32(sP + b * ATT_P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + s * ATT_KV_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 1024, 0);
-          const uint64_t db = make_smem_desc_sw128(v_addr + kk * 2048, 1024, 8192);
-          umma_f16(tmem_O, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_O, make_smem_desc_sw128(p_addr + k * 32, 1024, 0),
+                   make_smem_desc_sw128(v_addr + k * 2048, 1024, 8192), idesc_o, (j | k) != 0 ? 1u : 0u);
         umma_commit(&v_empty[s]);
-        umma_commit(pv_done);
-        if (j + 1 < p.n_kv) issue_s(j + 1);
+        umma_commit(&pv_done[b]);
+        if (j + 2 < p.n_kv) issue_s(j + 2);
       }
     }
   } else {
@@ -146,16 +159,18 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
     float m_used = -CUDART_INF_F;
     float l_run = 0.f;
     for (int j = 0; j < p.n_kv; ++j) {
-      const int valid = p.S - j * 128;  // keys [0, valid) of this block are real
-      const bool tail = valid < 128;    // warp-uniform: only the last key block of an image can be partial
-      mbar_wait(s_full, j & 1, 17);
+      const int b = j & 1;
+      const uint32_t tmem_S = tmem_base + b * 64 + lane_sel;
+      const int valid = p.S - j * ATT_BKV;  // keys [0, valid) of this block are real
+      const bool tail = valid < ATT_BKV;    // warp-uniform: only the last key block of an image can be partial
+      mbar_wait(&s_full[b], (j >> 1) & 1, 17);
       tc_fence_after();
       // pass 1: row maximum
       float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_x32(tmem_S + c * 32, v);
         tmem_ld_wait();
         if (tail) {
 #pragma unroll
@@ -171,34 +186,34 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         m_used = m_blk;
       else
         raise = m_blk > m_used + 8.0f;
-      if (j > 0) {
-        // P_{j-1} V_{j-1} must have retired before P is overwritten (and before O is touched)
-        mbar_wait(pv_done, (j - 1) & 1, 18);
+      if (j > 0 && __any_sync(0xffffffffu, raise)) {
+        // every MMA that has touched O so far must have retired before O is rewritten
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 18);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, raise)) {
-          const float m_new = raise ? m_blk : m_used;
-          const float alpha = exp2f(m_used - m_new);
-          m_used = m_new;
-          l_run *= alpha;
+        const float m_new = raise ? m_blk : m_used;
+        const float alpha = fast_exp2(m_used - m_new);
+        m_used = m_new;
+        l_run *= alpha;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
-            tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_O + lane_sel + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_x32(tmem_O + lane_sel + c * 32, v);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_x32(tmem_O + lane_sel + c * 32, v);
         }
+        tmem_st_wait();
       }
+      if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1, 19);  // P buffer b free: P_{j-2} V_{j-2} retired
       // pass 2: probabilities -> fp16 -> swizzled smem
       float lsum = 0.f;
       const float neg_m = -m_used;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      uint8_t* prow = sP + b * ATT_P_BYTES + r * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_x32(tmem_S + c * 32, v);
         tmem_ld_wait();
         if (tail) {
 #pragma unroll
@@ -208,16 +223,15 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
-          const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
           lsum += p0 + p1;
           __half2 h = __floats2half2_rn(p0, p1);
           packed[i] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          const int chunk = (c * 4 + q) ^ (r & 7);
           *reinterpret_cast<uint4*>(prow + chunk * 16) =
               make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
@@ -225,9 +239,9 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
       l_run += lsum;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[b]);
     }
-    mbar_wait(pv_done, (p.n_kv - 1) & 1, 19);
+    mbar_wait(&pv_done[(p.n_kv - 1) & 1], ((p.n_kv - 1) >> 1) & 1, 20);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int q = q0 + r;
@@ -340,13 +354,19 @@ attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, in
   for (int k = 0; k < 32; ++k) {
     s[k] = -CUDART_INF_F;
     if (k < F) {  // warp-uniform
-      float acc = 0.f;
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains: the dot product is latency bound otherwise
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float2 kk = __half22float2(*reinterpret_cast<const __half2*>(&sK[warp][k][2 * i]));
-        acc += q[2 * i] * kk.x + q[2 * i + 1] * kk.y;
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(&sK[warp][k][8 * i]);  // broadcast 16-byte read
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 kk = __half22float2(h[t]);
+          a4[t] = fmaf(q[8 * i + 2 * t], kk.x, a4[t]);
+          a4[t] = fmaf(q[8 * i + 2 * t + 1], kk.y, a4[t]);
+        }
       }
-      acc *= scale_log2;
+      float acc = ((a4[0] + a4[1]) + (a4[2] + a4[3])) * scale_log2;
       s[k] = acc;
       mx = fmaxf(mx, acc);
     }
@@ -358,14 +378,19 @@ attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, in
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     if (k < F) {
-      const float pr = exp2f(s[k] - mx);
+      const float pr = fast_exp2(s[k] - mx);
       l += pr;
       const float prh = __half2float(__float2half_rn(pr));
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float2 vv = __half22float2(*reinterpret_cast<const __half2*>(&sV[warp][k][2 * i]));
-        o[2 * i] += prh * vv.x;
-        o[2 * i + 1] += prh * vv.y;
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(&sV[warp][k][8 * i]);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 vv = __half22float2(h[t]);
+          o[8 * i + 2 * t] = fmaf(prh, vv.x, o[8 * i + 2 * t]);
+          o[8 * i + 2 * t + 1] = fmaf(prh, vv.y, o[8 * i + 2 * t + 1]);
+        }
       }
     }
   }
@@ -400,7 +425,7 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
   SVDPP_CHECK_ARG(d->q_off % 8 == 0 && d->k_off % 8 == 0 && d->v_off % 8 == 0, "attn: offsets must be multiples of 8");
   AttnParams p{};
   p.S = d->S;
-  p.n_kv = (d->S + 127) / 128;
+  p.n_kv = (d->S + ATT_BKV - 1) / ATT_BKV;
   p.q_off = d->q_off;
   p.k_off = d->k_off;
   p.v_off = d->v_off;
@@ -415,19 +440,21 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
   }
   SVDPP_CHECK_ARG(impl == 0, "attn: unknown impl %d", impl);
   SVDPP_CHECK_ARG(d->heads <= 65535 && d->n_img <= 65535, "attn: grid too large");
-  CUtensorMap tm;
+  CUtensorMap tmQ, tmKV;
   const long long rows = static_cast<long long>(d->n_img) * d->S;
   uint64_t dims[2] = {static_cast<uint64_t>(d->ld), static_cast<uint64_t>(rows)};
   uint64_t str[1] = {static_cast<uint64_t>(d->ld) * 2};
-  uint32_t box[2] = {64, 128};
-  if (encode_tmap_f16(&tm, d->qkv, 2, dims, str, box)) return -5;
+  uint32_t box_q[2] = {64, 128};
+  uint32_t box_kv[2] = {64, ATT_BKV};
+  if (encode_tmap_f16(&tmQ, d->qkv, 2, dims, str, box_q)) return -5;
+  if (encode_tmap_f16(&tmKV, d->qkv, 2, dims, str, box_kv)) return -5;
   static bool configured = false;
   if (!configured) {
     SVDPP_CUDA(cudaFuncSetAttribute(attn_spatial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     configured = true;
   }
   dim3 grid((d->S + 127) / 128, d->heads, d->n_img);
-  attn_spatial_tc_kernel<<<grid, 192, ATT_SMEM_BYTES, stream>>>(tm, p);
+  attn_spatial_tc_kernel<<<grid, 192, ATT_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
   return check_launch("attn_spatial_tc_kernel");
 }
 

@@ -44,12 +44,12 @@ struct GemmParams {
 // third of erff()'s cost, which otherwise makes the GEGLU epilogue slower than its K=320 main loop.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
-  const float half_erfc = 0.5f * poly * t * exp2f(z * z * -1.4426950408889634f);  // 0.5*erfc(|x|/sqrt2)
+  const float half_erfc = 0.5f * poly * t * fast_exp2(z * z * -1.4426950408889634f);  // 0.5*erfc(|x|/sqrt2)
   const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   return x * phi;
 }
@@ -60,6 +60,14 @@ __device__ __forceinline__ __half geglu_fp16(float val, float gate) {
   __half g16 = __float2half_rn(gate);
   __half ge = __float2half_rn(gelu_erf(__half2float(g16)));
   return __hmul(v16, ge);
+}
+// Two columns at once: packed f32->f16x2 conversions and one HMUL2 (scalar F2F conversions are
+// quarter-rate and were the epilogue's bottleneck).
+__device__ __forceinline__ __half2 geglu_fp16x2(float v0, float v1, float g0, float g1) {
+  const __half2 v16 = __floats2half2_rn(v0, v1);
+  const float2 gr = __half22float2(__floats2half2_rn(g0, g1));
+  const __half2 ge = __floats2half2_rn(gelu_erf(gr.x), gelu_erf(gr.y));
+  return __hmul2(v16, ge);
 }
 
 __device__ __forceinline__ void load8(const __half* p, float (&o)[8]) {
@@ -86,7 +94,7 @@ struct GemmCfg {
   // accesses (row pitch 336 B / 176 B) hit 32 distinct banks
   static constexpr int C_PITCH = NOUT + 8;
   static constexpr int C_BYTES = BM * C_PITCH * 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 512 /*barriers + bias tile*/;
 };
 
 template <int BN, bool GEGLU>
@@ -102,6 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 128);  // [BN] this tile's bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,7 +144,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // Lane 0 owns the ring (waits, expect_tx, the B tile); in conv mode lane r < nrows issues the
-    // window box of image row r, whose coordinates are computed once per tile.
+    // window box of image row r, whose coordinates are computed once per tile.  Keep this loop lean: the
+    // warp issues one k-block every ~320 cycles at peak.  (Tried and removed: an L2 prefetch stream 16 k-blocks
+    // ahead via cp.async.bulk.prefetch.tensor lowered throughput by ~40 % on B200.)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -238,7 +249,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool m_ok = m < p.M;
       const int nout0 = n_tile * Cfg::NOUT;
       const bool vec_ok = (p.ldd & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
+      // bias of this tile's BN weight rows -> smem (a global load per chunk stalled the epilogue ~500
+      // cycles each, several times the K = 320 main loop)
+      if (et < BN / 8) {
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (p.bias != nullptr) bv = *reinterpret_cast<const uint4*>(p.bias + n_tile * BN + et * 8);
+        *reinterpret_cast<uint4*>(sBias + et * 8) = bv;
+      }
+      // per-image row vector of this thread's row and column chunks -> registers, before the wait
+      uint4 rvv[Cfg::NOUT / CW / 2][CW / 8];
+      bool has_rv = false;
       if constexpr (!GEGLU) {
+        if (p.rowvec != nullptr && m_ok) {
+          has_rv = true;
+          const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
+          const __half* rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN;
+#pragma unroll
+          for (int ci = 0; ci < Cfg::NOUT / CW / 2; ++ci) {
+            const int c = half + 2 * ci;
+#pragma unroll
+            for (int hlf = 0; hlf < CW / 8; ++hlf)
+              rvv[ci][hlf] = (nout0 + c * CW < p.n_store) ? *reinterpret_cast<const uint4*>(rv + c * CW + hlf * 8)
+                                                          : make_uint4(0, 0, 0, 0);
+          }
+        }
         if (p.R1 != nullptr) {
           const bool r_vec = (p.ldr1 & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
           constexpr int NV = Cfg::BM * VPR / 256;  // vectors per thread (10): all loads in flight at once
@@ -266,20 +300,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int r = i / VPR, v = i - r * VPR;
             *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
           }
-          epi_bar();
         }
       }
+      epi_bar();
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + as * Cfg::ACC_STRIDE;
-      const __half* rv = nullptr;
-      if (p.rowvec != nullptr && m_ok) {
-        const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
-        rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld;
-      }
       __half* srow = sC + row * Cfg::C_PITCH;
-#pragma unroll 1
-      for (int c = half; c < Cfg::NOUT / CW; c += 2) {
+#pragma unroll
+      for (int ci = 0; ci < Cfg::NOUT / CW / 2; ++ci) {
+        const int c = half + 2 * ci;
         uint32_t v[CW];
         uint32_t g[CW];
         if constexpr (GEGLU) {
@@ -289,39 +319,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_x16(taddr + c * CW, v);
         }
         tmem_ld_wait();
-        const int nw = n_tile * BN + c * CW;  // weight-row index of the value columns
-        const int nout = nout0 + c * CW;      // output column
+        const int nout = nout0 + c * CW;  // output column
         float y[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+        {
           float b8[8];
 #pragma unroll
           for (int hlf = 0; hlf < CW / 8; ++hlf) {
-            load8(p.bias + nw + hlf * 8, b8);
+            load8(sBias + c * CW + hlf * 8, b8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
           }
         }
-        __half o[CW];
+        __align__(16) __half o[CW];
         if constexpr (GEGLU) {
           float gt[CW];
 #pragma unroll
           for (int j = 0; j < CW; ++j) gt[j] = __uint_as_float(g[j]);
-          if (p.bias != nullptr) {
+          {
             float b8[8];
-            load8(p.bias + nw + BN / 2, b8);
+            load8(sBias + BN / 2 + c * CW, b8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) gt[j] += b8[j];
           }
 #pragma unroll
-          for (int j = 0; j < CW; ++j) o[j] = geglu_fp16(y[j], gt[j]);
+          for (int j = 0; j < CW; j += 2)
+            *reinterpret_cast<__half2*>(&o[j]) = geglu_fp16x2(y[j], y[j + 1], gt[j], gt[j + 1]);
         } else {
-          if (rv != nullptr && nout < p.n_store) {
-            float b8[8];
+          if (has_rv) {
 #pragma unroll
             for (int hlf = 0; hlf < CW / 8; ++hlf) {
-              load8(rv + nw + hlf * 8, b8);
+              float b8[8];
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rvv[ci][hlf]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                b8[2 * j] = f.x;
+                b8[2 * j + 1] = f.y;
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
             }
@@ -347,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
 #pragma unroll
-          for (int j = 0; j < CW; ++j) o[j] = __float2half_rn(y[j]);
+          for (int j = 0; j < CW; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
         }
         uint4* d4 = reinterpret_cast<uint4*>(srow + c * CW);
         const uint4* o4 = reinterpret_cast<const uint4*>(o);

@@ -7,11 +7,13 @@ holds the whole model, owns a contiguous slice of the step schedule, receives th
 
 What differs from the reference is *how* the handoff is issued, not what is exchanged:
 
-* the receive buffer is a persistent pair (``LatentSpec.empty`` once per slot, reference allocates per
+* the receive buffer is a persistent pair (``LatentSpec.empty`` once per slot; the reference allocates per
   sample at ``pipeline.py:76``);
-* ``run_many`` pre-posts the receive for sample ``k+1`` before computing sample ``k`` and sends with
-  ``isend``, so on NCCL the 1.8 MB latent crosses NVLink while the stage computes (the reference's
-  blocking ``send``/``recv`` pair at ``pipeline.py:78,84`` serialises them on gloo);
+* ``run_many`` issues ``isend``/``irecv`` and waits on the *stream* (``work.wait()``), never on the host:
+  the host keeps enqueueing the next video's steps while the GPU finishes the exchange.  The exchange is
+  deliberately not left pending across compute: an NCCL send/recv kernel that spins for its peer occupies
+  SMs, and the persistent one-CTA-per-SM kernels of this path would then run a whole extra wave.  The
+  1.8 MB latent costs microseconds on NVLink against >= 100 ms of compute per stage and video;
 * ``PipelineConfig.allow_uneven`` opts into ``assign_steps_uneven`` (the reference raises, Q1).
 
 Message order, tags, shapes and the values exchanged are identical, so a mixed world of reference
@@ -149,7 +151,6 @@ class PipelineStage:
             raise ValueError("rank 0 requires an input_supplier when processing multiple samples")
         last = cfg.rank == cfg.world_size - 1
         outputs: List[torch.Tensor] = []
-        pending = self._post_recv() if cfg.rank > 0 else None
         for sample_idx in range(num_samples):
             if cfg.rank == 0:
                 latent = input_supplier(sample_idx)
@@ -157,17 +158,17 @@ class PipelineStage:
                     raise ValueError("rank 0 requires an input latent tensor")
                 latent = latent.to(cfg.latent_spec.device)
             else:
-                work, buf = pending
+                work, buf = self._post_recv()
                 work.wait()
-                # the slot is rewritten two samples later; the model returns a fresh tensor per
-                # step, but an empty stage would forward the slot itself, hence the clone there
+                # the slot is rewritten two samples later; the model returns a fresh tensor per step,
+                # but an empty stage would forward the slot itself, hence the clone there
                 latent = buf if self.step_range.count else buf.clone()
-                pending = self._post_recv() if sample_idx + 1 < num_samples else None
             latent = self._run_local_steps(latent)
             if last:
                 outputs.append(latent)
             else:
                 self._send_latent(latent, blocking=False)
+                self._drain_send()      # stream-ordered wait: later kernels queue behind the send
         self._drain_send()
         return outputs if outputs else None
 
