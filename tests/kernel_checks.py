@@ -295,6 +295,8 @@ ALL_CHECKS = {
     "linear_small": lambda: linear_small(),
     "layernorm": lambda: layernorm(),
     "layernorm_1280": lambda: layernorm(M=33, C=1280, add=False),
+    "layernorm_640": lambda: layernorm(M=37, C=640, add=True),
+    "layernorm_generic": lambda: layernorm(M=19, C=128, add=True),
     "groupnorm": lambda: groupnorm(),
     "groupnorm_cat": lambda: groupnorm(n_img=2, HW=144, C1=128, C2=64),
     "groupnorm_temporal": lambda: groupnorm(n_img=6, HW=50, C1=320, fps=3, eps=1e-6, silu=False),

@@ -36,7 +36,8 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // owns the 8 channels [8*tx, 8*tx+8) and walks the pixels ty, ty+rows, ... of a 64-pixel chunk, so
 // consecutive threads touch consecutive 16-byte vectors (also across pixel boundaries) and per-channel
 // quantities (running sums, or scale/shift) live in registers.  grid = (chunks, images).
-constexpr int GN_PIX_PER_CHUNK = 64;
+constexpr int GN_PIX_PER_CHUNK = 64;   // statistics pass (fixes the workspace layout); larger chunks measured slower
+constexpr int GN_APPLY_PIX = 64;       // apply pass
 constexpr int GN_GROUPS = 32;
 
 __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const __half* x2, int C2, long long pix,
@@ -58,13 +59,23 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  for (int p = p0 + threadIdx.y; p < p1; p += rows) {
-    float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, static_cast<long long>(n) * HW + p, c0)), v);
+  for (int pb = p0 + threadIdx.y; pb < p1; pb += 4 * rows) {
+    uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += v[j];
-      ss[j] += v[j] * v[j];
+    for (int t = 0; t < 4; ++t) {  // four independent 16-byte loads in flight
+      const int p = pb + t * rows;
+      u[t] = p < p1 ? *reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, static_cast<long long>(n) * HW + p, c0))
+                    : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float v[8];
+      unpack8(u[t], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        ss[j] += v[j] * v[j];
+      }
     }
   }
 #pragma unroll
@@ -126,8 +137,8 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * GN_PIX_PER_CHUNK;
-  const int p1 = min(p0 + GN_PIX_PER_CHUNK, HW);
+  const int p0 = blockIdx.x * GN_APPLY_PIX;
+  const int p1 = min(p0 + GN_APPLY_PIX, HW);
   const int cpg = C / GN_GROUPS;
   const float2* st = stats + (n / frames_per_stat) * GN_GROUPS;
   float sc[8], sh[8];
@@ -142,16 +153,27 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
       sh[j] = b[j] - mr.x * sc[j];
     }
   }
-  for (int p = p0 + threadIdx.y; p < p1; p += rows) {
-    const long long pix = static_cast<long long>(n) * HW + p;
-    float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, pix, c0)), v);
+  for (int pb = p0 + threadIdx.y; pb < p1; pb += 4 * rows) {
+    uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float y = fmaf(v[j], sc[j], sh[j]);
-      v[j] = silu ? silu_f(y) : y;
+    for (int t = 0; t < 4; ++t) {  // four independent 16-byte loads in flight
+      const int p = pb + t * rows;
+      if (p < p1) u[t] = *reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, static_cast<long long>(n) * HW + p, c0));
     }
-    *reinterpret_cast<uint4*>(out + pix * C + c0) = pack8(v);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int p = pb + t * rows;
+      if (p < p1) {
+        float v[8];
+        unpack8(u[t], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(v[j], sc[j], sh[j]);
+          v[j] = silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * HW + p) * C + c0) = pack8(v);
+      }
+    }
   }
 }
 
@@ -213,6 +235,67 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, const __half* __re
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = (v[k][j] - mean) * rstd * g[j] + b[j];
       *reinterpret_cast<uint4*>(out + m * ldo + vi * 8) = pack8(y);
+    }
+  }
+}
+
+// C = 40 * LPR channels (320 / 640 / 1280): LPR lanes per row, 5 vectors per lane, 32/LPR rows per warp, so
+// every lane has 5 independent 16-byte loads in flight (the generic kernel leaves 3/4 of the lanes idle on
+// the second vector at C = 320).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
+                      int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                      __half* __restrict__ out, long long ldo, int M, float eps) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int C = 40 * LPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const long long m = (static_cast<long long>(blockIdx.x) * 8 + warp) * RPW + sub;
+  const bool active = m < M;
+  const __half* xr = x + (active ? m : 0) * ldx;
+  const __half* ar = addvec ? addvec + static_cast<long long>(((active ? m : 0) / add_hw) % add_mod) * C : nullptr;
+  float v[5][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) unpack8(*reinterpret_cast<const uint4*>(xr + (li + k * LPR) * 8), v[k]);
+  if (ar) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(ar + (li + k * LPR) * 8), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = __half2float(__float2half_rn(v[k][j] + a[j]));  // fp16 add, as torch
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[k][j];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[k][j] - mean;
+      sq += d * d;
+    }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / C + eps);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int c0 = (li + k * LPR) * 8;
+      float g[8], b[8], y[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
+      unpack8(*reinterpret_cast<const uint4*>(beta + c0), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[k][j] - mean) * rstd * g[j] + b[j];
+      *reinterpret_cast<uint4*>(out + m * ldo + c0) = pack8(y);
     }
   }
 }
@@ -516,7 +599,8 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
   gn_finalize_kernel<<<n_stats, 256, 0, stream>>>(partial, n_chunks, frames_per_stat, count, eps, stats);
   if (int e = check_launch("gn_finalize_kernel")) return e;
-  gn_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
+  dim3 grid_apply((HW + GN_APPLY_PIX - 1) / GN_APPLY_PIX, n_img);
+  gn_apply_kernel<<<grid_apply, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                               stats, static_cast<__half*>(out), HW, frames_per_stat, apply_silu);
   return check_launch("gn_apply_kernel");
@@ -530,11 +614,20 @@ extern "C" int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, i
   SVDPP_CHECK_ARG(C % 8 == 0 && C <= LN_MAX_VEC * 256, "layernorm: C=%d unsupported", C);
   SVDPP_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0, "layernorm: pitches must be multiples of 8");
   if (addvec) SVDPP_CHECK_ARG(add_hw > 0 && add_mod > 0, "layernorm: bad addvec indexing");
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, stream>>>(static_cast<const __half*>(x), ldx,
-                                                    static_cast<const __half*>(addvec), add_hw > 0 ? add_hw : 1,
-                                                    add_mod > 0 ? add_mod : 1, static_cast<const __half*>(gamma),
-                                                    static_cast<const __half*>(beta), static_cast<__half*>(out), ldo,
-                                                    M, C, eps);
+  const __half* xh = static_cast<const __half*>(x);
+  const __half* ah = static_cast<const __half*>(addvec);
+  const __half* gh = static_cast<const __half*>(gamma);
+  const __half* bh = static_cast<const __half*>(beta);
+  __half* oh = static_cast<__half*>(out);
+  const int hw = add_hw > 0 ? add_hw : 1, md = add_mod > 0 ? add_mod : 1;
+  if (C == 320)
+    layernorm_rows_kernel<8><<<(M + 31) / 32, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+  else if (C == 640)
+    layernorm_rows_kernel<16><<<(M + 15) / 16, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+  else if (C == 1280)
+    layernorm_rows_kernel<32><<<(M + 7) / 8, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+  else
+    layernorm_kernel<<<(M + 7) / 8, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, C, eps);
   return check_launch("layernorm_kernel");
 }
 

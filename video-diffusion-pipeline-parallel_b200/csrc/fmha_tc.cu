@@ -223,8 +223,10 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
+          const float x0 = fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m);
+          const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);  // (poly_exp2 for a quarter of these was measured 7 % slower: issue-bound)
           lsum += p0 + p1;
           __half2 h = __floats2half2_rn(p0, p1);
           packed[i] = *reinterpret_cast<uint32_t*>(&h);
@@ -308,15 +310,19 @@ __global__ void attn_spatial_simt_kernel(const __half* qkv, long long ld, AttnPa
   for (int i = 0; i < 64; ++i) dst[i] = __float2half_rn(o[i] / l);
 }
 
-// Temporal attention: warp per (batch, pixel, head); lane = frame.
+// Temporal attention: warp per (batch, pixel, head); lane = frame.  K and V rows are converted to fp32 once
+// when staged in smem, so the two F x 64 inner products are pure LDS.128 + FFMA.
+constexpr int TATT_WARPS = 4;
+constexpr int TATT_PITCH = 68;  // floats per staged row (272 B, 16-byte aligned, spreads banks)
 __global__ void __launch_bounds__(128)
 attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, int k_off, int v_off,
                      __half* __restrict__ out, long long ldo, int B, int F, int HW, int heads, float scale_log2) {
-  __shared__ __align__(16) __half sK[4][32][72];  // padded rows (144 B) to spread banks
-  __shared__ __align__(16) __half sV[4][32][72];
+  extern __shared__ __align__(16) float tsm[];  // [warps][2][32][PITCH]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long unit = static_cast<long long>(blockIdx.x) * 4 + warp;
+  float* sK = tsm + warp * 2 * 32 * TATT_PITCH;
+  float* sV = sK + 32 * TATT_PITCH;
+  const long long unit = static_cast<long long>(blockIdx.x) * TATT_WARPS + warp;
   const long long total = static_cast<long long>(B) * HW * heads;
   if (unit >= total) return;
   const int head = static_cast<int>(unit % heads);
@@ -331,19 +337,38 @@ attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, in
     const uint4* qp = reinterpret_cast<const uint4*>(base + q_off);
     const uint4* kp = reinterpret_cast<const uint4*>(base + k_off);
     const uint4* vp = reinterpret_cast<const uint4*>(base + v_off);
+    uint4 qu[8], ku[8], vu[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // 24 independent 16-byte loads in flight per lane
+      qu[i] = qp[i];
+      ku[i] = kp[i];
+      vu[i] = vp[i];
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      uint4 u = qp[i];
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+      const __half2* hq = reinterpret_cast<const __half2*>(&qu[i]);
+      const __half2* hk = reinterpret_cast<const __half2*>(&ku[i]);
+      const __half2* hv = reinterpret_cast<const __half2*>(&vu[i]);
+      float kf[8], vf[8];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 f = __half22float2(h[t]);
-        q[i * 8 + 2 * t] = f.x;
-        q[i * 8 + 2 * t + 1] = f.y;
+        const float2 fq = __half22float2(hq[t]);
+        const float2 fk = __half22float2(hk[t]);
+        const float2 fv = __half22float2(hv[t]);
+        q[i * 8 + 2 * t] = fq.x * scale_log2;   // fold the softmax scale into q
+        q[i * 8 + 2 * t + 1] = fq.y * scale_log2;
+        kf[2 * t] = fk.x;
+        kf[2 * t + 1] = fk.y;
+        vf[2 * t] = fv.x;
+        vf[2 * t + 1] = fv.y;
       }
       if (active) {
-        *reinterpret_cast<uint4*>(&sK[warp][lane][i * 8]) = kp[i];
-        *reinterpret_cast<uint4*>(&sV[warp][lane][i * 8]) = vp[i];
+        float4* dk = reinterpret_cast<float4*>(sK + lane * TATT_PITCH + i * 8);
+        float4* dv = reinterpret_cast<float4*>(sV + lane * TATT_PITCH + i * 8);
+        dk[0] = make_float4(kf[0], kf[1], kf[2], kf[3]);
+        dk[1] = make_float4(kf[4], kf[5], kf[6], kf[7]);
+        dv[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
+        dv[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
       }
     }
   }
@@ -354,19 +379,17 @@ attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, in
   for (int k = 0; k < 32; ++k) {
     s[k] = -CUDART_INF_F;
     if (k < F) {  // warp-uniform
-      float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains: the dot product is latency bound otherwise
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* kr = reinterpret_cast<const float4*>(sK + k * TATT_PITCH);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = *reinterpret_cast<const uint4*>(&sK[warp][k][8 * i]);  // broadcast 16-byte read
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 kk = __half22float2(h[t]);
-          a4[t] = fmaf(q[8 * i + 2 * t], kk.x, a4[t]);
-          a4[t] = fmaf(q[8 * i + 2 * t + 1], kk.y, a4[t]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float4 kk = kr[i];  // broadcast read
+        a4[0] = fmaf(q[4 * i], kk.x, a4[0]);
+        a4[1] = fmaf(q[4 * i + 1], kk.y, a4[1]);
+        a4[2] = fmaf(q[4 * i + 2], kk.z, a4[2]);
+        a4[3] = fmaf(q[4 * i + 3], kk.w, a4[3]);
       }
-      float acc = ((a4[0] + a4[1]) + (a4[2] + a4[3])) * scale_log2;
+      const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
       s[k] = acc;
       mx = fmaxf(mx, acc);
     }
@@ -381,16 +404,14 @@ attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, in
       const float pr = fast_exp2(s[k] - mx);
       l += pr;
       const float prh = __half2float(__float2half_rn(pr));
+      const float4* vr = reinterpret_cast<const float4*>(sV + k * TATT_PITCH);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = *reinterpret_cast<const uint4*>(&sV[warp][k][8 * i]);
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 vv = __half22float2(h[t]);
-          o[8 * i + 2 * t] = fmaf(prh, vv.x, o[8 * i + 2 * t]);
-          o[8 * i + 2 * t + 1] = fmaf(prh, vv.y, o[8 * i + 2 * t + 1]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float4 vv = vr[i];
+        o[4 * i] = fmaf(prh, vv.x, o[4 * i]);
+        o[4 * i + 1] = fmaf(prh, vv.y, o[4 * i + 1]);
+        o[4 * i + 2] = fmaf(prh, vv.z, o[4 * i + 2]);
+        o[4 * i + 3] = fmaf(prh, vv.w, o[4 * i + 3]);
       }
     }
   }
@@ -468,7 +489,13 @@ extern "C" int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_of
                   "attn_temporal: pitches/offsets must be multiples of 8");
   const long long units = static_cast<long long>(B) * HW * heads;
   const unsigned blocks = static_cast<unsigned>((units + 3) / 4);
-  attn_temporal_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off, v_off,
+  constexpr int tsm_bytes = TATT_WARPS * 2 * 32 * TATT_PITCH * sizeof(float);  // 69632
+  static bool configured_t = false;
+  if (!configured_t) {
+    SVDPP_CUDA(cudaFuncSetAttribute(attn_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm_bytes));
+    configured_t = true;
+  }
+  attn_temporal_kernel<<<blocks, 128, tsm_bytes, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off, v_off,
                                                    static_cast<__half*>(out), ldo, B, F, HW, heads,
                                                    scale * 1.4426950408889634f);
   return check_launch("attn_temporal_kernel");
