@@ -7,6 +7,9 @@ Workload: SVD-XT, 25 frames, 576x1024 (latent 72x128), 25 Euler steps, random-in
 One bench "step" = one video through all 25 denoising steps.  With N GPUs the 25 steps are split into
 N pipeline stages (uneven split allowed) and K*N videos are streamed, so per-GPU work is fixed
 ("weak").  value = videos/min over the whole timed region (pipeline fill and drain included).
+Stage placement for N>1 is --schedule ring by default (stage s of video v on rank (v+s)%N, see
+PipelineStage.run_many_ring); the reference's fixed placement is timed as well and reported under
+"linear_pipeline".
 
 Reference arm:
   python bench.py --impl reference ...   times the CPU restatement of the reference's step (oracle/) on
@@ -46,6 +49,9 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-frames", type=int, default=2)
+    p.add_argument("--schedule", default="ring", choices=["ring", "linear"],
+                   help="N>1: 'ring' rotates the stage->rank placement per video (no fill/drain bubble, no stage "
+                        "imbalance); 'linear' is the reference's fixed placement (stage s on rank s)")
     return p.parse_args()
 
 
@@ -230,20 +236,30 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: first video eager, second captures the per-step CUDA graphs, third replays
-    warm_in = make_inputs(Wm, 1000) if rank == 0 else None
-    stage.run_many(Wm, input_supplier=(lambda i: warm_in[i]) if rank == 0 else None)
+    ring = world > 1 and args.schedule == "ring"
+
+    def run_stream(n, supplier):
+        """Stream n videos; returns the latents that finished on this rank."""
+        if ring:
+            return [o for _, o in stage.run_many_ring(n, input_supplier=supplier)]
+        return stage.run_many(n, input_supplier=supplier if rank == 0 else None) or []
+
+    # ---- warm-up: first step eager, then one CUDA graph per step index is captured, then replays
+    n_warm = Wm * world if ring else Wm
+    warm_in = {i: t for i, t in zip(range(n_warm), make_inputs(n_warm, 1000))} if (ring or rank == 0) else {}
+    run_stream(n_warm, lambda i: warm_in[i])
+    del warm_in
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
-    inputs = make_inputs(n_videos, 0) if rank == 0 else None
+    inputs = make_inputs(n_videos, 0) if (ring or rank == 0) else None
     sampler = ClockSampler(local_rank)
     launches0 = native.LAUNCHES
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    outs = stage.run_many(n_videos, input_supplier=(lambda i: inputs[i]) if rank == 0 else None)
+    outs = run_stream(n_videos, lambda i: inputs[i])
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -254,38 +270,58 @@ def main() -> None:
     launches = torch.tensor([native.LAUNCHES - launches0], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(launches)
-    finite = bool(torch.isfinite(outs[-1]).all()) if last else True
+    finite = all(bool(torch.isfinite(o).all()) for o in outs)
 
     # ---- timed region 2: end to end through the public API with host buffers
+    need_in = ring or rank == 0
     host_in = [torch.randn(shape, dtype=torch.float32).half().mul_(model.init_noise_sigma).pin_memory()
-               for _ in range(n_videos)] if rank == 0 else None
-    host_out = torch.empty(shape, dtype=torch.float16).pin_memory() if last else None
+               if (need_in and (not ring or i % world == rank)) else None for i in range(n_videos)]
+    host_out = torch.empty(shape, dtype=torch.float16).pin_memory() if (ring or last) else None
 
     def supply_from_host(i):
         return host_in[i].to(dev, non_blocking=True)
 
     barrier()
     t0 = time.perf_counter()
-    for i in range(n_videos):
-        if rank == 0:
-            lat = supply_from_host(i)
-        else:
-            work, buf = stage._post_recv()
-            work.wait()
-            lat = buf if stage.step_range.count else buf.clone()
-        lat = stage._run_local_steps(lat)
-        if last:
+    if ring:
+        for _, lat in stage.run_many_ring(n_videos, input_supplier=supply_from_host):
             host_out.copy_(lat, non_blocking=True)
-            torch.cuda.synchronize()
-        else:
-            stage._send_latent(lat, blocking=False)
-            stage._drain_send()
-    stage._drain_send()
+        torch.cuda.synchronize()
+    else:
+        for i in range(n_videos):
+            if rank == 0:
+                lat = supply_from_host(i)
+            else:
+                work, buf = stage._post_recv()
+                work.wait()
+                lat = buf if stage.step_range.count else buf.clone()
+            lat = stage._run_local_steps(lat)
+            if last:
+                host_out.copy_(lat, non_blocking=True)
+                torch.cuda.synchronize()
+            else:
+                stage._send_latent(lat, blocking=False)
+                stage._drain_send()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+
+    # ---- N>1: the reference's fixed stage placement on the same stream, for comparison
+    linear_value = None
+    if ring:
+        n_lin = 2 * world
+        lin_in = make_inputs(n_lin, 500) if rank == 0 else None
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        stage.run_many(n_lin, input_supplier=(lambda i: lin_in[i]) if rank == 0 else None)
+        l1.record()
+        barrier()
+        lms = torch.tensor([l0.elapsed_time(l1)], device=dev)
+        dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+        linear_value = n_lin / (float(lms.item()) / 1000.0) * 60.0
     bytes_lat = shape.numel() * 2
 
     if rank == 0:
@@ -301,7 +337,8 @@ def main() -> None:
                             f"1524623082 params, dummy conditioning, "
                             f"{'CFG %.1f batch 2' % args.guidance_scale if args.guidance_scale else 'no CFG'}",
                 "videos_timed": n_videos, "stage_sizes": stage_sizes(T, world),
-                "parallelism": f"step-pipeline x{world}" if world > 1 else "single GPU",
+                "parallelism": (f"step-pipeline x{world}, {'rotating (ring)' if ring else 'fixed (reference)'} stage "
+                                f"placement") if world > 1 else "single GPU",
                 "cuda_graph": model.use_cuda_graph,
                 "l2": "per-step working set (3 GB weights + >10 GB activations) exceeds the 126 MB L2; no flush needed",
             },
@@ -313,11 +350,14 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_lat, "d2h_bytes_per_step": bytes_lat},
             "model_build_s": round(t_build, 1),
         }
+        if linear_value is not None:
+            result["linear_pipeline"] = {"value": linear_value, "unit": UNIT, "videos_timed": 2 * world,
+                                         "note": "reference placement (stage s on rank s), fill/drain included"}
     # ---- roofline of the dominant kernel (tcgen05 GEMM/conv family), instrumented eager pass, rank 0
     if rank == 0:
         model.use_cuda_graph = False
         native.PROFILE = []
-        x = inputs[0]
+        x = make_inputs(1, 0)[0]
         torch.cuda.synchronize()
         model(x, 0)
         torch.cuda.synchronize()

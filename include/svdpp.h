@@ -66,7 +66,8 @@ typedef struct svdpp_gemm_desc {
   int32_t n_store;                        /* store columns n < n_store (after geglu halving) */
 } svdpp_gemm_desc;
 
-/* impl: 0 = tcgen05 kernel (the product), 1 = plain CUDA-core kernel (slow; bring-up cross-check) */
+/* impl: 0 = tcgen05 kernel, one CTA per tile; 2 = tcgen05 kernel with CTA pairs (cta_group::2, 256-row tiles);
+ *       1 = plain CUDA-core kernel (slow; bring-up cross-check) */
 int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -33,6 +33,10 @@ def _cmp(got: torch.Tensor, ref: torch.Tensor, rel=2e-3, floor=1e-3):
     return dict(max_err=err, tol=tol, cos=cos, ref_absmax=ref.abs().max().item(), ok=bool(finite and err <= tol))
 
 
+def _bn(impl):
+    return 256 if impl == 3 else native.GEMM_BN
+
+
 def _pad_n(w, mult=native.GEMM_BN):
     n = w.shape[0]
     npad = (n + mult - 1) // mult * mult
@@ -49,7 +53,7 @@ def gemm_linear(M=300, N=320, K=320, impl=0, epilogue="full", split=False):
     w = _rand(N, K, scale=K ** -0.5, seed=2)
     bias = _rand(N, seed=3)
     out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
-    kw = dict(bias=_pad_n(bias))
+    kw = dict(bias=_pad_n(bias, _bn(impl)))
     ref = a.float() @ w.float().t() + bias.float()
     if epilogue == "full":
         hw, div, mod = 7, 2, 5
@@ -61,9 +65,9 @@ def gemm_linear(M=300, N=320, K=320, impl=0, epilogue="full", split=False):
     if split:
         k1 = (K // 2) // 64 * 64
         a1, a2 = a[:, :k1].contiguous(), a[:, k1:].contiguous()
-        native.gemm(out, a1, _pad_n(w), a2=a2, n_store=N, impl=impl, **kw)
+        native.gemm(out, a1, _pad_n(w, _bn(impl)), a2=a2, n_store=N, impl=impl, **kw)
     else:
-        native.gemm(out, a, _pad_n(w), n_store=N, impl=impl, **kw)
+        native.gemm(out, a, _pad_n(w, _bn(impl)), n_store=N, impl=impl, **kw)
     torch.cuda.synchronize()
     return _cmp(out, ref)
 
@@ -73,7 +77,7 @@ def gemm_geglu(M=260, C=128, impl=0):
     a = _rand(M, C, seed=1)
     w = _rand(2 * inner, C, scale=C ** -0.5, seed=2)
     b = _rand(2 * inner, scale=0.1, seed=3)
-    wi, bi, n = interleave_geglu(w, b)
+    wi, bi, n = interleave_geglu(w, b, half=128 if impl == 3 else 80)
     out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.float16)
     native.gemm(out, a, wi, bias=bi, geglu=True, n_store=inner, impl=impl)
     y = (a.float() @ w.float().t() + b.float()).half()
@@ -87,9 +91,9 @@ def conv3x3(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
     x = _rand(B * Fr, H, W, C, seed=1)                      # channels-last
     w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
     b = _rand(Cout, seed=3)
-    wk = _pad_n(w.permute(0, 2, 3, 1).reshape(Cout, -1))
+    wk = _pad_n(w.permute(0, 2, 3, 1).reshape(Cout, -1), _bn(impl))
     out = torch.full((B * Fr * H * W, Cout), float("nan"), device=DEV, dtype=torch.float16)
-    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_3X3,
+    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_3X3,
                 n_store=Cout, impl=impl)
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
@@ -100,9 +104,9 @@ def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
     x = _rand(B, Fr, H, W, C, seed=1)
     w = _rand(C, C, 3, 1, 1, scale=(3 * C) ** -0.5, seed=2)
     b = _rand(C, seed=3)
-    wk = _pad_n(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(C, -1))
+    wk = _pad_n(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(C, -1), _bn(impl))
     out = torch.full((B * Fr * H * W, C), float("nan"), device=DEV, dtype=torch.float16)
-    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_T3,
+    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, H, W, C), taps=native.TAPS_T3,
                 n_store=C, impl=impl)
     ref = F.conv3d(x.permute(0, 4, 1, 2, 3).float(), w.float(), b.float(), padding=(1, 0, 0)).permute(0, 2, 3, 4, 1)
     torch.cuda.synchronize()
@@ -319,6 +323,21 @@ ALL_CHECKS = {
     "tc_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=160, impl=0),
     "tc_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=64, impl=0),
     "tc_conv_temporal": lambda: conv_temporal(impl=0),
+    "pair_gemm_plain": lambda: gemm_linear(M=256, N=160, K=64, impl=2, epilogue="bias"),
+    "pair_gemm_linear": lambda: gemm_linear(impl=2),
+    "pair_gemm_big": lambda: gemm_linear(M=4000, N=640, K=1280, impl=2),
+    "pair_gemm_split": lambda: gemm_linear(impl=2, K=384, split=True),
+    "pair_gemm_geglu_320": lambda: gemm_geglu(M=1000, C=320, impl=2),
+    "pair_conv3x3_w32": lambda: conv3x3(impl=2),
+    "pair_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=160, impl=2),
+    "pair_conv_temporal": lambda: conv_temporal(impl=2),
+    "pair256_gemm_plain": lambda: gemm_linear(M=512, N=256, K=64, impl=3, epilogue="bias"),
+    "pair256_gemm_linear": lambda: gemm_linear(M=300, N=1280, K=320, impl=3),
+    "pair256_gemm_big": lambda: gemm_linear(M=4000, N=1280, K=1280, impl=3),
+    "pair256_gemm_split": lambda: gemm_linear(M=700, N=512, impl=3, K=384, split=True),
+    "pair256_gemm_geglu_320": lambda: gemm_geglu(M=1000, C=320, impl=3),
+    "pair256_conv3x3_w32": lambda: conv3x3(Cout=256, impl=3),
+    "pair256_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=256, impl=3),
     "tc_attn_spatial_256": lambda: attn_spatial(n_img=1, S=256, heads=1, impl=0),
     "tc_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=0),
     "tc_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=0),
@@ -397,6 +416,8 @@ UNET_CHECKS = {
     "unet_tiny_tc_gemm": lambda: unet_tiny(0, 1),
     "unet_tiny_tc": lambda: unet_tiny(0, 0),
     "unet_tiny_tc_b2": lambda: unet_tiny(0, 0, B=2, Fr=2, H=16, W=32),
+    "unet_tiny_pair": lambda: unet_tiny(2, 0),
+    "unet_tiny_pair256": lambda: unet_tiny(3, 0, cfg_over=dict(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))),
     "svd_steps_simt": lambda: svd_steps(gemm_impl=1, attn_impl=1),
     "svd_steps_tc": lambda: svd_steps(),
     "svd_steps_tc_cfg": lambda: svd_steps(cfg_scale=3.0),

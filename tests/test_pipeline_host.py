@@ -123,6 +123,35 @@ def _worker(rank, world, port, total_steps, n_samples, uneven, use_run_many, q):
     finalize_distributed()
 
 
+def _ring_worker(rank, world, port, total_steps, n_samples, q):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    torch.set_num_threads(1)
+    init_distributed(backend="gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    ts = list(reversed(range(total_steps)))
+    stage = PipelineStage(_model(), PipelineConfig(total_steps, world, rank, ts, _spec(), allow_uneven=True))
+    with torch.no_grad():
+        outs = stage.run_many_ring(n_samples, input_supplier=_supplier)
+    q.put([(v, _sha(o)) for v, o in outs])
+    dist.barrier()
+    finalize_distributed()
+
+
+def _run_ring(world, total_steps, n_samples):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, total_steps, n_samples, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        got.update(dict(q.get(timeout=180)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return [got[v] for v in range(n_samples)]
+
+
 def _run_world(world, total_steps, n_samples=3, uneven=False, use_run_many=True):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -164,3 +193,11 @@ def test_world_size_invariance_uneven_split():
     want = _single_process(25)
     assert _run_world(2, 25, uneven=True) == want
     assert _run_world(4, 25, uneven=True) == want          # stages of 7, 6, 6, 6 steps (BASELINE config 1)
+
+
+@pytest.mark.timeout(300)
+def test_ring_placement_matches_single_process():
+    """Rotating stage placement: every video still sees the steps in order; 25 steps on 4 ranks (7,6,6,6),
+    5 videos (a partial last round), bit-identical to running each video alone."""
+    assert _run_ring(4, 25, 5) == _single_process(25, 5)
+    assert _run_ring(2, 28, 4) == _single_process(28, 4)

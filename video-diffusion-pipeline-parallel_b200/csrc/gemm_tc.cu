@@ -81,27 +81,34 @@ __device__ __forceinline__ void load8(const __half* p, float (&o)[8]) {
   }
 }
 
-template <int BN, bool GEGLU>
+// TWO: CTA pairs (cta_group::2).  The pair computes a 256 x BN tile: each CTA loads its own 128 rows of A
+// and HALF of the B tile, the leader issues M = 256 MMAs that read B from both CTAs' smem, and each CTA
+// keeps the accumulator of its own 128 rows in its own TMEM.  Per SM and k-block this moves 26 KB instead of
+// 36 KB from L2 (the L2 -> SM path, not the tensor pipe, caps the one-CTA kernel near 1 PFLOP/s).
+template <int BN, bool GEGLU, bool TWO>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = TWO ? BN / 2 : BN;  // B rows this CTA loads
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 160) ? 5 : 4;
+  static constexpr int STAGES = (TWO && BN <= 160) ? 6 : 5;
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
   static constexpr int NOUT = GEGLU ? BN / 2 : BN;
-  // epilogue staging tile [128][NOUT + 8] fp16: the 16-byte pad makes a quarter-warp's 16-byte row
-  // accesses (row pitch 336 B / 176 B) hit 32 distinct banks
-  static constexpr int C_PITCH = NOUT + 8;
+  // epilogue staging tile [128][SW + 8] fp16, SW output columns per round (a 256-wide tile is staged in two
+  // rounds of 128): the 16-byte pad makes a quarter-warp's 16-byte row accesses hit 32 distinct banks
+  static constexpr int ROUNDS = NOUT > 160 ? 2 : 1;
+  static constexpr int SW = NOUT / ROUNDS;
+  static constexpr int C_PITCH = SW + 8;
   static constexpr int C_BYTES = BM * C_PITCH * 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 512 /*barriers + bias tile*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 1024 /*barriers + bias tile*/;
 };
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, bool TWO>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, GEGLU>;
+  using Cfg = GemmCfg<BN, GEGLU, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __half* sC = reinterpret_cast<__half*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -114,7 +121,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work item = one tile (or, for CTA pairs, two vertically adjacent tiles sharing the N tile)
+  const int cta_rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+  const int work_first = TWO ? (blockIdx.x >> 1) : blockIdx.x;
+  const int work_stride = TWO ? (gridDim.x >> 1) : gridDim.x;
+  const int work_total = TWO ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  auto m_tile_of = [&](int w) { return TWO ? 2 * (w / p.n_tiles) + cta_rank : w / p.n_tiles; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -123,21 +135,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], TWO ? 2 : 1);  // pairs: both producers arrive on the leader's barrier
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 256);
+      mbar_init(&tempty[s], TWO ? 512 : 256);  // pairs: both CTAs' epilogue threads, on the leader
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc2(tmem_slot, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO)
+    cluster_sync_all();
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -149,9 +169,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ahead via cp.async.bulk.prefetch.tensor lowered throughput by ~40 % on B200.)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * Cfg::BM;
-      const int n0 = (tile % p.n_tiles) * BN;
+    for (int w = work_first; w < work_total; w += work_stride) {
+      const int m0 = m_tile_of(w) * Cfg::BM;
+      const int n0 = (w % p.n_tiles) * BN + cta_rank * Cfg::B_ROWS;
       int cw = 0, ch = 0, cf = 0, cb = 0;
       if (p.conv && lane < p.nrows) {
         const int px = m0 + lane * p.bw;
@@ -168,20 +188,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sb = sa + Cfg::A_BYTES;
         if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
-          if (!p.conv) {
-            if (kb < p.kb_split)
-              tma_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
+          if constexpr (TWO) {
+            if (cta_rank == 0)
+              mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land on this barrier
             else
-              tma_load_2d(sa, &tmA2, &full[stage], (kb - p.kb_split) * 64, m0);
+              mbar_arrive_cluster(&full[stage], 0);
+            tma2_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
+            if (!p.conv) {
+              if (kb < p.kb_split)
+                tma2_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
+              else
+                tma2_load_2d(sa, &tmA2, &full[stage], (kb - p.kb_split) * 64, m0);
+            }
+          } else {
+            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
+            if (!p.conv) {
+              if (kb < p.kb_split)
+                tma_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
+              else
+                tma_load_2d(sa, &tmA2, &full[stage], (kb - p.kb_split) * 64, m0);
+            }
           }
         }
         __syncwarp();
         if (p.conv) {
-          if (lane < p.nrows)
-            tma_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
-                        ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+          if (lane < p.nrows) {
+            if constexpr (TWO)
+              tma2_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
+                           ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+            else
+              tma_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
+                          ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+          }
           if (++kc == p.cpk) {
             kc = 0;
             ++tap;
@@ -195,13 +234,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BN, false);
+    if (lane == 0 && cta_rank == 0) {  // pairs: only the leader issues (for both CTAs)
+      constexpr uint32_t idesc = make_idesc_f16(BN, false, TWO ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = work_first; w < work_total; w += work_stride) {
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
@@ -214,41 +253,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO)
+              umma2_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          if constexpr (TWO)
+            umma2_commit(&empty[stage]);
+          else
+            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete
+        if constexpr (TWO)
+          umma2_commit(&tfull[as]);
+        else
+          umma_commit(&tfull[as]);  // accumulator complete
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    // Per tile: (1) coalesced copy of the R1 residual tile into the staging buffer, (2) accumulator
-    // rows from TMEM, epilogue math, fp16 result back into the staging buffer (TMEM stage released
-    // here), (3) coalesced copy of the staging buffer to global.  Thread = accumulator row.
+    // Per tile and per round of SW output columns: (1) coalesced copy of the R1 residual columns into the
+    // staging buffer, (2) accumulator rows from TMEM, epilogue math, fp16 result back into the staging
+    // buffer (the TMEM stage is released after the last round), (3) coalesced copy of the staging buffer
+    // to global.  Thread = accumulator row; the two warps of a lane quarter take alternate column chunks.
     const int we = warp & 3;          // the TMEM lane quarter this warp may read (warp % 4)
     const int half = (warp - 4) >> 2;  // 0: even column chunks, 1: odd column chunks
     const int row = we * 32 + lane;
     const int et = threadIdx.x - 128;  // 0..255
-    constexpr int VPR = Cfg::NOUT / 8;  // 16-byte vectors per staged row
-    constexpr int CW = GEGLU ? 8 : 16;  // columns per chunk: 10 chunks either way, 5 per warp
+    constexpr int SW = Cfg::SW;
+    constexpr int VPR = SW / 8;         // 16-byte vectors per staged row
+    constexpr int CW = GEGLU ? 8 : 16;  // columns per chunk
+    constexpr int NCH = SW / CW / 2;    // chunks per warp and round
+    constexpr int NV = Cfg::BM * VPR / 256;  // staged vectors per thread
+    static_assert(Cfg::BM * VPR % 256 == 0 && (SW / CW) % 2 == 0, "epilogue work split");
     auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile % p.n_tiles;
+    for (int w = work_first; w < work_total; w += work_stride) {
+      const int m_tile = m_tile_of(w);
+      const int n_tile = w % p.n_tiles;
       const int m_base = m_tile * Cfg::BM;
       const int m = m_base + row;
       const bool m_ok = m < p.M;
-      const int nout0 = n_tile * Cfg::NOUT;
-      const bool vec_ok = (p.ldd & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
       // bias of this tile's BN weight rows -> smem (a global load per chunk stalled the epilogue ~500
       // cycles each, several times the K = 320 main loop)
       if (et < BN / 8) {
@@ -256,168 +307,186 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.bias != nullptr) bv = *reinterpret_cast<const uint4*>(p.bias + n_tile * BN + et * 8);
         *reinterpret_cast<uint4*>(sBias + et * 8) = bv;
       }
-      // per-image row vector of this thread's row and column chunks -> registers, before the wait
-      uint4 rvv[Cfg::NOUT / CW / 2][CW / 8];
-      bool has_rv = false;
+      const __half* rv_row = nullptr;
       if constexpr (!GEGLU) {
         if (p.rowvec != nullptr && m_ok) {
-          has_rv = true;
           const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
-          const __half* rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN;
-#pragma unroll
-          for (int ci = 0; ci < Cfg::NOUT / CW / 2; ++ci) {
-            const int c = half + 2 * ci;
-#pragma unroll
-            for (int hlf = 0; hlf < CW / 8; ++hlf)
-              rvv[ci][hlf] = (nout0 + c * CW < p.n_store) ? *reinterpret_cast<const uint4*>(rv + c * CW + hlf * 8)
-                                                          : make_uint4(0, 0, 0, 0);
-          }
-        }
-        if (p.R1 != nullptr) {
-          const bool r_vec = (p.ldr1 & 7) == 0 && nout0 + Cfg::NOUT <= p.n_store;
-          constexpr int NV = Cfg::BM * VPR / 256;  // vectors per thread (10): all loads in flight at once
-          static_assert(Cfg::BM * VPR % 256 == 0, "staging copy assumes a whole number of vectors per thread");
-          uint4 val[NV];
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const int i = et + k * 256;
-            const int r = i / VPR, v = i - r * VPR;
-            val[k] = make_uint4(0, 0, 0, 0);
-            if (m_base + r < p.M) {
-              const __half* src = p.R1 + static_cast<long long>(m_base + r) * p.ldr1 + nout0 + v * 8;
-              if (r_vec) {
-                val[k] = *reinterpret_cast<const uint4*>(src);
-              } else {
-                __half tmp[8];
-                for (int j = 0; j < 8; ++j) tmp[j] = (nout0 + v * 8 + j < p.n_store) ? src[j] : __float2half(0.f);
-                val[k] = *reinterpret_cast<uint4*>(tmp);
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const int i = et + k * 256;
-            const int r = i / VPR, v = i - r * VPR;
-            *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
-          }
+          rv_row = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN;
         }
       }
-      epi_bar();
-      mbar_wait(&tfull[as], aphase, 4);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + as * Cfg::ACC_STRIDE;
       __half* srow = sC + row * Cfg::C_PITCH;
+#pragma unroll 1
+      for (int rd = 0; rd < Cfg::ROUNDS; ++rd) {
+        const int col0 = rd * SW;                       // first column of this round within the tile
+        const int nout0 = n_tile * Cfg::NOUT + col0;    // ... and in the output matrix
+        const bool vec_ok = (p.ldd & 7) == 0 && nout0 + SW <= p.n_store;
+        // per-image row vector of this thread's row and chunks -> registers, before any wait
+        uint4 rvv[NCH][CW / 8];
+        if constexpr (!GEGLU) {
+          if (rv_row != nullptr) {
 #pragma unroll
-      for (int ci = 0; ci < Cfg::NOUT / CW / 2; ++ci) {
-        const int c = half + 2 * ci;
-        uint32_t v[CW];
-        uint32_t g[CW];
-        if constexpr (GEGLU) {
-          tmem_ld_x8(taddr + c * CW, v);
-          tmem_ld_x8(taddr + BN / 2 + c * CW, g);
-        } else {
-          tmem_ld_x16(taddr + c * CW, v);
-        }
-        tmem_ld_wait();
-        const int nout = nout0 + c * CW;  // output column
-        float y[CW];
+            for (int ci = 0; ci < NCH; ++ci) {
+              const int c = half + 2 * ci;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]);
-        {
-          float b8[8];
+              for (int hlf = 0; hlf < CW / 8; ++hlf)
+                rvv[ci][hlf] = (nout0 + c * CW < p.n_store)
+                                   ? *reinterpret_cast<const uint4*>(rv_row + col0 + c * CW + hlf * 8)
+                                   : make_uint4(0, 0, 0, 0);
+            }
+          }
+          if (p.R1 != nullptr) {
+            const bool r_vec = (p.ldr1 & 7) == 0 && nout0 + SW <= p.n_store;
+            uint4 val[NV];  // all loads in flight at once
 #pragma unroll
-          for (int hlf = 0; hlf < CW / 8; ++hlf) {
-            load8(sBias + c * CW + hlf * 8, b8);
+            for (int k = 0; k < NV; ++k) {
+              const int i = et + k * 256;
+              const int r = i / VPR, v = i - r * VPR;
+              val[k] = make_uint4(0, 0, 0, 0);
+              if (m_base + r < p.M) {
+                const __half* src = p.R1 + static_cast<long long>(m_base + r) * p.ldr1 + nout0 + v * 8;
+                if (r_vec) {
+                  val[k] = *reinterpret_cast<const uint4*>(src);
+                } else {
+                  __half tmp[8];
+                  for (int j = 0; j < 8; ++j) tmp[j] = (nout0 + v * 8 + j < p.n_store) ? src[j] : __float2half(0.f);
+                  val[k] = *reinterpret_cast<uint4*>(tmp);
+                }
+              }
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+            for (int k = 0; k < NV; ++k) {
+              const int i = et + k * 256;
+              const int r = i / VPR, v = i - r * VPR;
+              *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
+            }
           }
         }
-        __align__(16) __half o[CW];
-        if constexpr (GEGLU) {
-          float gt[CW];
+        epi_bar();
+        if (rd == 0) {
+          mbar_wait(&tfull[as], aphase, 4);
+          tc_fence_after();
+        }
 #pragma unroll
-          for (int j = 0; j < CW; ++j) gt[j] = __uint_as_float(g[j]);
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = half + 2 * ci;
+          uint32_t v[CW];
+          uint32_t g[CW];
+          if constexpr (GEGLU) {
+            tmem_ld_x8(taddr + col0 + c * CW, v);
+            tmem_ld_x8(taddr + BN / 2 + col0 + c * CW, g);
+          } else {
+            tmem_ld_x16(taddr + col0 + c * CW, v);
+          }
+          tmem_ld_wait();
+          const int nout = nout0 + c * CW;  // output column
+          float y[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]);
           {
             float b8[8];
-            load8(sBias + BN / 2 + c * CW, b8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gt[j] += b8[j];
-          }
-#pragma unroll
-          for (int j = 0; j < CW; j += 2)
-            *reinterpret_cast<__half2*>(&o[j]) = geglu_fp16x2(y[j], y[j + 1], gt[j], gt[j + 1]);
-        } else {
-          if (has_rv) {
 #pragma unroll
             for (int hlf = 0; hlf < CW / 8; ++hlf) {
-              float b8[8];
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rvv[ci][hlf]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                b8[2 * j] = f.x;
-                b8[2 * j + 1] = f.y;
-              }
+              load8(sBias + col0 + c * CW + hlf * 8, b8);
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
             }
           }
+          __align__(16) __half o[CW];
+          if constexpr (GEGLU) {
+            float gt[CW];
 #pragma unroll
-          for (int j = 0; j < CW; ++j) y[j] *= p.alpha;
-          if (p.R1 != nullptr) {
-            float b8[8];
+            for (int j = 0; j < CW; ++j) gt[j] = __uint_as_float(g[j]);
+            {
+              float b8[8];
+              load8(sBias + BN / 2 + col0 + c * CW, b8);
 #pragma unroll
-            for (int hlf = 0; hlf < CW / 8; ++hlf) {
-              load8(srow + c * CW + hlf * 8, b8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
+              for (int j = 0; j < 8; ++j) gt[j] += b8[j];
             }
-          }
-          if (p.R2 != nullptr && m_ok && nout < p.n_store) {
-            float b8[8];
 #pragma unroll
-            for (int hlf = 0; hlf < CW / 8; ++hlf) {
-              load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < CW; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
-        }
-        uint4* d4 = reinterpret_cast<uint4*>(srow + c * CW);
-        const uint4* o4 = reinterpret_cast<const uint4*>(o);
-#pragma unroll
-        for (int q = 0; q < CW / 8; ++q) d4[q] = o4[q];
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);  // accumulator stage free: the next tile's MMAs may start
-      epi_bar();
-      for (int i = et; i < Cfg::BM * VPR; i += 256) {
-        const int r = i / VPR, v = i - r * VPR;
-        if (m_base + r < p.M) {
-          const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
-          __half* dst = p.D + static_cast<long long>(m_base + r) * p.ldd + nout0 + v * 8;
-          if (vec_ok) {
-            *reinterpret_cast<uint4*>(dst) = val;
+            for (int j = 0; j < CW; j += 2)
+              *reinterpret_cast<__half2*>(&o[j]) = geglu_fp16x2(y[j], y[j + 1], gt[j], gt[j + 1]);
           } else {
-            const __half* hv = reinterpret_cast<const __half*>(&val);
-            for (int j = 0; j < 8; ++j)
-              if (nout0 + v * 8 + j < p.n_store) dst[j] = hv[j];
+            if (rv_row != nullptr) {
+#pragma unroll
+              for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rvv[ci][hlf]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h2[j]);
+                  y[hlf * 8 + 2 * j] += f.x;
+                  y[hlf * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] *= p.alpha;
+            if (p.R1 != nullptr) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                load8(srow + c * CW + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
+              }
+            }
+            if (p.R2 != nullptr && m_ok && nout < p.n_store) {
+              float b8[8];
+#pragma unroll
+              for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < CW; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(srow + c * CW);
+          const uint4* o4 = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < CW / 8; ++q) d4[q] = o4[q];
+        }
+        if (rd == Cfg::ROUNDS - 1) {
+          tc_fence_before();
+          if constexpr (TWO)
+            mbar_arrive_cluster(&tempty[as], 0);
+          else
+            mbar_arrive(&tempty[as]);  // accumulator stage free: the next tile's MMAs may start
+        }
+        epi_bar();
+        for (int i = et; i < Cfg::BM * VPR; i += 256) {
+          const int r = i / VPR, v = i - r * VPR;
+          if (m_base + r < p.M) {
+            const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
+            __half* dst = p.D + static_cast<long long>(m_base + r) * p.ldd + nout0 + v * 8;
+            if (vec_ok) {
+              *reinterpret_cast<uint4*>(dst) = val;
+            } else {
+              const __half* hv = reinterpret_cast<const __half*>(&val);
+              for (int j = 0; j < 8; ++j)
+                if (nout0 + v * 8 + j < p.n_store) dst[j] = hv[j];
+            }
           }
         }
+        epi_bar();  // staging buffer reusable
       }
-      epi_bar();  // staging buffer reusable
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO)
+    cluster_sync_all();
+  else
+    __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (TWO)
+      tmem_dealloc2(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -501,15 +570,34 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   e.D[static_cast<long long>(m) * e.ldd + nout] = o;
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, bool TWO>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, GEGLU>;
+  using Cfg = GemmCfg<BN, GEGLU, TWO>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, GEGLU>;
+  auto kern = gemm_tc_kernel<BN, GEGLU, TWO>;
   if (!configured) {
     SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
+  }
+  if constexpr (TWO) {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    int clusters = num_sms() / 2;
+    if (pairs < clusters) clusters = pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SVDPP_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, p));
+    return check_launch("gemm_tc_kernel<pair>");
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
@@ -523,8 +611,9 @@ using namespace svdpp;
 
 extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  constexpr int BN = 160;
   SVDPP_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  // impl 3: CTA pairs with 256-wide tiles (N must be a multiple of 256; GEGLU weights interleaved per 128)
+  const int BN = impl == 3 ? 256 : 160;
   SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
   SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
   SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
@@ -570,6 +659,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     p.cW = d->cW;
   }
 
+  if (impl == 3) {
+    SVDPP_CHECK_ARG(d->N % 256 == 0, "gemm: impl 3 needs N %% 256 == 0 (N=%d)", d->N);
+  }
   if (impl == 1) {
     SimtParams sp{};
     sp.M = d->M;
@@ -600,7 +692,8 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
     return check_launch("gemm_simt_kernel");
   }
-  SVDPP_CHECK_ARG(impl == 0, "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "gemm: unknown impl %d", impl);
+  const bool two = impl >= 2;  // CTA pairs (cta_group::2)
 
   CUtensorMap tmA, tmA2, tmB;
   if (!d->conv) {
@@ -643,9 +736,17 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     SVDPP_CHECK_ARG(d->ldw % 8 == 0, "gemm: ldw must be a multiple of 8");
     uint64_t dims[2] = {static_cast<uint64_t>(d->K), static_cast<uint64_t>(d->N)};
     uint64_t str[1] = {static_cast<uint64_t>(d->ldw) * 2};
-    uint32_t box[2] = {64, BN};
+    uint32_t box[2] = {64, static_cast<uint32_t>(two ? BN / 2 : BN)};
     if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
   }
-  if (d->geglu) return launch_tc<BN, true>(tmA, tmA2, tmB, p, stream);
-  return launch_tc<BN, false>(tmA, tmA2, tmB, p, stream);
+  if (impl == 3) {
+    if (d->geglu) return launch_tc<256, true, true>(tmA, tmA2, tmB, p, stream);
+    return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
+  }
+  if (two) {
+    if (d->geglu) return launch_tc<160, true, true>(tmA, tmA2, tmB, p, stream);
+    return launch_tc<160, false, true>(tmA, tmA2, tmB, p, stream);
+  }
+  if (d->geglu) return launch_tc<160, true, false>(tmA, tmA2, tmB, p, stream);
+  return launch_tc<160, false, false>(tmA, tmA2, tmB, p, stream);
 }

@@ -21,6 +21,7 @@ torch is used for allocation, one-time weight repacking and CUDA streams.  There
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Mapping, Optional, Sequence, Tuple
 
 import torch
@@ -61,20 +62,23 @@ def _pad_cols(w: torch.Tensor, mult: int = 64) -> torch.Tensor:
     return out
 
 
-def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
+def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor], half: int = _HALF_BN
+                     ) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
     """[2*inner, K] (value rows then gate rows, diffusers GEGLU chunk order) -> rows grouped per
-    160-row tile as [80 value | 80 gate], inner padded to a multiple of 80.  Returns (w, b, inner)."""
+    (2*half)-row tile as [half value | half gate] (half = 80 for the 160-wide kernel, 128 for the 256-wide
+    CTA-pair kernel), inner padded to a multiple of half.  Returns (w, b, inner)."""
     inner = w.shape[0] // 2
-    inner_pad = _ceil_to(inner, _HALF_BN)
-    tiles = inner_pad // _HALF_BN
+    _HALF = half
+    inner_pad = _ceil_to(inner, _HALF)
+    tiles = inner_pad // _HALF
 
     def one(t: torch.Tensor) -> torch.Tensor:
         val, gate = t[:inner], t[inner:]
         tail = (inner_pad - inner,) + tuple(t.shape[1:])
         z = torch.zeros(tail, dtype=t.dtype, device=t.device)
         val, gate = torch.cat([val, z]), torch.cat([gate, z])
-        val = val.reshape((tiles, _HALF_BN) + tuple(t.shape[1:]))
-        gate = gate.reshape((tiles, _HALF_BN) + tuple(t.shape[1:]))
+        val = val.reshape((tiles, _HALF) + tuple(t.shape[1:]))
+        gate = gate.reshape((tiles, _HALF) + tuple(t.shape[1:]))
         return torch.cat([val, gate], dim=1).reshape((2 * inner_pad,) + tuple(t.shape[1:])).contiguous()
 
     return one(w), (one(b) if b is not None else None), inner
@@ -82,10 +86,10 @@ def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.
 
 class _Lin:
     """A packed [N_pad, K_pad] weight with optional bias and its true output width."""
-    __slots__ = ("w", "b", "n", "geglu")
+    __slots__ = ("w", "b", "n", "geglu", "impl")
 
-    def __init__(self, w, b, n, geglu=False):
-        self.w, self.b, self.n, self.geglu = w, b, n, geglu
+    def __init__(self, w, b, n, geglu=False, impl=None):
+        self.w, self.b, self.n, self.geglu, self.impl = w, b, n, geglu, impl
 
 
 def window_path_ok(W: int, C: int) -> bool:
@@ -95,7 +99,7 @@ def window_path_ok(W: int, C: int) -> bool:
 
 class NativeUNet(nn.Module):
     def __init__(self, state_dict: Mapping[str, torch.Tensor], config: Optional[dict] = None,
-                 device: torch.device | str = "cuda", gemm_impl: int = 0, attn_impl: int = 0):
+                 device: torch.device | str = "cuda", gemm_impl: Optional[int] = None, attn_impl: int = 0):
         super().__init__()
         self.cfg = dict(SVD_CONFIG)
         if config:
@@ -104,7 +108,9 @@ class NativeUNet(nn.Module):
         if self.device_.type != "cuda":
             raise NativeError("NativeUNet needs a CUDA device (there is no CPU path)")
         native.load()
-        self.gemm_impl = gemm_impl
+        # 0: one CTA per 128x160 tile; 2: CTA pairs (cta_group::2), 256x160; 3: CTA pairs with 256x256 tiles where
+        # N % 256 == 0 and the one-CTA kernel elsewhere; SVDPP_GEMM_IMPL overrides the default for experiments
+        self.gemm_impl = int(os.environ.get("SVDPP_GEMM_IMPL", "3")) if gemm_impl is None else gemm_impl
         self.attn_impl = attn_impl
         self.dtype = torch.float16
         self._sd = state_dict
@@ -146,8 +152,12 @@ class NativeUNet(nn.Module):
         return _Lin(self._keep(_pad_rows(w)), self._keep(_pad_rows(self._g(prefix + ".bias"))), w.shape[0])
 
     def _geglu(self, prefix: str) -> _Lin:
-        w, b, inner = interleave_geglu(self._g(prefix + ".weight"), self._g(prefix + ".bias"))
-        return _Lin(self._keep(w), self._keep(b), inner, geglu=True)
+        w, b = self._g(prefix + ".weight"), self._g(prefix + ".bias")
+        if self.gemm_impl == 3 and (w.shape[0] // 2) % 128 == 0:      # packed for the 256-wide pair kernel
+            w, b, inner = interleave_geglu(w, b, half=128)
+            return _Lin(self._keep(w), self._keep(b), inner, geglu=True, impl=3)
+        w, b, inner = interleave_geglu(w, b)
+        return _Lin(self._keep(w), self._keep(b), inner, geglu=True, impl=0 if self.gemm_impl == 3 else None)
 
     def _norm(self, prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
         return self._keep(self._g(prefix + ".weight").contiguous()), self._keep(self._g(prefix + ".bias").contiguous())
@@ -264,11 +274,18 @@ class NativeUNet(nn.Module):
         return native.groupnorm_silu(out, x1, norm[0], norm[1], n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2,
                                      frames_per_stat=fps, workspace=self._gn_ws)
 
+    def _impl(self, lin: _Lin) -> int:
+        if lin.impl is not None:
+            return lin.impl
+        if self.gemm_impl == 3:
+            return 3 if lin.w.shape[0] % 256 == 0 else 0
+        return self.gemm_impl
+
     def _linear(self, a, lin: _Lin, *, a2=None, **epi):
         n_out = lin.n
         out = self._new(a.shape[0], n_out)
         return native.gemm(out, a, lin.w, bias=lin.b, a2=a2, geglu=lin.geglu, n_store=n_out,
-                           impl=self.gemm_impl, **epi)
+                           impl=self._impl(lin), **epi)
 
     def _conv(self, a, lin: _Lin, dims, taps, **epi):
         B, F, H, W, C = dims
@@ -276,10 +293,10 @@ class NativeUNet(nn.Module):
         out = self._new(M, lin.n)
         if window_path_ok(W, C):
             return native.gemm(out, a, lin.w, bias=lin.b, conv_dims=dims, taps=taps, n_store=lin.n,
-                               impl=self.gemm_impl, **epi)
+                               impl=self._impl(lin), **epi)
         cols = self._new(M, len(taps) * C)
         native.im2col(cols, a, B=B, F=F, H=H, W=W, Cc=C, Ho=H, Wo=W, stride=1, taps=taps)
-        return native.gemm(out, cols, lin.w, bias=lin.b, n_store=lin.n, impl=self.gemm_impl, **epi)
+        return native.gemm(out, cols, lin.w, bias=lin.b, n_store=lin.n, impl=self._impl(lin), **epi)
 
     def _small_mlp(self, x, l1, l2, x_add=None):
         h = self._new(x.shape[0], l1[0].shape[0])
@@ -377,7 +394,7 @@ class NativeUNet(nn.Module):
         cols = self._new(x_in.shape[0], self.conv_in.w.shape[1])
         native.im2col(cols, x_in, B=B, F=F, H=H, W=W, Cc=cin, Ho=H, Wo=W, stride=1, taps=TAPS_3X3)
         x = native.gemm(self._new(x_in.shape[0], self.conv_in.n), cols, self.conv_in.w, bias=self.conv_in.b,
-                        n_store=self.conv_in.n, impl=self.gemm_impl)
+                        n_store=self.conv_in.n, impl=self._impl(self.conv_in))
         skips = [x]
         h, w = H, W
         for blk in self.down:

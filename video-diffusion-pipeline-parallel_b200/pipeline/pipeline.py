@@ -172,6 +172,62 @@ class PipelineStage:
         self._drain_send()
         return outputs if outputs else None
 
+    def run_many_ring(self, num_samples: int, *, input_supplier: InputSupplier
+                      ) -> List[tuple]:
+        """Rotating stage placement (extension; same step slices, same per-video arithmetic).
+
+        The reference pins stage s to rank s, so a stream of videos pays a fill/drain bubble of
+        ``world-1`` stage times and, with an uneven split (25 steps on 8 stages), every stage waits for
+        the longest one.  Every rank holds the whole model, so here stage s of video v runs on rank
+        ``(v + s) % world``: in time slot t *all* ranks run stage t (equal length by construction) on
+        ``world`` different videos, then all latents hop one rank along the ring.  No bubble, no
+        imbalance; each video still flows through the stages in order with one handoff per boundary.
+
+        Every rank calls ``input_supplier(v)`` for the videos it starts (v % world == rank).  Returns
+        the ``(video index, final latent)`` pairs that finished on this rank.
+        """
+        if num_samples <= 0:
+            raise ValueError("num_samples must be positive for pipeline execution")
+        if input_supplier is None:
+            raise ValueError("ring placement needs an input_supplier on every rank")
+        cfg = self.config
+        W, r = cfg.world_size, cfg.rank
+        split = assign_steps_uneven if cfg.allow_uneven else assign_steps
+        stages = [split(cfg.total_steps, W, s) for s in range(W)]
+        outputs: List[tuple] = []
+        n_batches = (num_samples + W - 1) // W
+        for b in range(n_batches):
+            cur: Optional[torch.Tensor] = None
+            for t in range(W):
+                v = b * W + (r - t) % W
+                exists = v < num_samples
+                if t == 0 and exists:
+                    cur = input_supplier(v)
+                    if cur is None:
+                        raise ValueError("input_supplier returned None")
+                    cur = cur.to(cfg.latent_spec.device)
+                if exists:
+                    for step in cfg.timesteps[stages[t].start: stages[t].end]:
+                        cur = self.model(cur, step)
+                if t == W - 1:
+                    if exists:
+                        outputs.append((v, cur))
+                    break
+                # hop: my video goes to rank+1, the video of rank-1 comes to me (both at stage t -> t+1)
+                v_in = b * W + (r - 1 - t) % W
+                ops = []
+                if exists:
+                    ops.append(dist.P2POp(dist.isend, cur.contiguous(), (r + 1) % W))
+                buf = None
+                if v_in < num_samples:
+                    buf = self._next_recv_slot()
+                    ops.append(dist.P2POp(dist.irecv, buf, (r - 1) % W))
+                if ops:
+                    for work in dist.batch_isend_irecv(ops):
+                        work.wait()
+                cur = buf
+        return outputs
+
     def _process_single_latent(self, input_latent: Optional[torch.Tensor],
                                sample_idx: Optional[int]) -> Optional[torch.Tensor]:
         """recv -> local steps -> send for one sample (reference ``pipeline.py:134-157``; called
