@@ -53,14 +53,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same, but the hardware may keep the thread suspended for up to `ns` before returning false
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (launch error, process survives) instead of hanging the box.
-#ifndef SVDPP_SPIN_LIMIT
-#define SVDPP_SPIN_LIMIT (1u << 22)
+// Waiting threads sleep in hardware (suspend-time hint) instead of re-issuing try_wait: in the first FMHA
+// profile a quarter of all issue slots went to the spin loop of waiting warps.
+#ifndef SVDPP_WAIT_TRIES
+#define SVDPP_WAIT_TRIES 40000u   // x 100 us hint = 4 s
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SVDPP_SPIN_LIMIT) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t tries = 0;
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+    if (++tries > SVDPP_WAIT_TRIES) {
       printf("svdpp: mbarrier timeout tag=%d block=(%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
              blockIdx.y, threadIdx.x, parity);
       __trap();
