@@ -96,7 +96,8 @@ int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t 
 /* GroupNorm(32 groups) [+ SiLU] over channels-last input that may be the channel concatenation
  * [x1 (C1) | x2 (C2)] (the up-block skip cat); statistics per (image, group), or per
  * (frames_per_stat consecutive images, group) for the temporal ResBlock's 5-D GroupNorm.
- * out is [n_img*HW, C1+C2].  workspace >= svdpp_groupnorm_workspace_bytes(). Deterministic.
+ * out is [n_img*HW, C1+C2].  workspace >= svdpp_groupnorm_workspace_bytes(), its first 16 KB ZERO-FILLED before the first
+ * use (it holds arrival counters that every call leaves at zero again).  Deterministic: fixed summation order.
  * Replaces: nn.GroupNorm + SiLU in ResnetBlock2D / TemporalResnetBlock / transformer norm / conv_norm_out. */
 size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW);
 int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
@@ -116,6 +117,18 @@ int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, int32_t add_
 int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y,
                        int64_t ldy, int32_t R, int32_t N, int32_t K, int32_t act_in, int32_t act_out,
                        svdpp_stream stream);
+
+/* n_groups independent small linears in one launch: for group g (a device array of descriptors),
+ *   y[r, y_off + n] = sum_k x[r, x_off + k] * W[n, k] + bias[n],  n < N, k < K  (K, x_off multiples of 8).
+ * Used for the output projections of the 1-token cross-attention of all transformer blocks at once
+ * (attn2.to_out of BasicTransformerBlock / TemporalBasicTransformerBlock). max_n = max over groups of N. */
+typedef struct svdpp_small_group {
+  const void* W;      /* device, [N, K] fp16, K contiguous */
+  const void* bias;   /* device, [N] fp16 or NULL */
+  int32_t x_off, y_off, N, K;
+} svdpp_small_group;
+int svdpp_linear_small_grouped(const void* x, int64_t ldx, const svdpp_small_group* groups_dev, int32_t n_groups,
+                               int32_t max_n, void* y, int64_t ldy, int32_t R, svdpp_stream stream);
 
 /* Sinusoidal embedding [cos | sin] (flip_sin_to_cos, shift 0) of n_vals scalars into [n_vals, dim] fp16.
  * src_kind: 0 = fp32 device array, 1 = fp16 device array, 2 = the integers (i % src_mod). */

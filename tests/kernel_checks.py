@@ -153,9 +153,11 @@ def groupnorm(n_img=4, HW=100, C1=64, C2=0, fps=1, silu=True, eps=1e-5):
     C = C1 + C2
     g, b = _rand(C, seed=3), _rand(C, seed=4)
     out = torch.full((n_img * HW, C), float("nan"), device=DEV, dtype=torch.float16)
-    ws = torch.empty(native.groupnorm_workspace_bytes(n_img, HW) // 4 + 1, dtype=torch.float32, device=DEV)
-    native.groupnorm_silu(out, x1, g, b, n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2, frames_per_stat=fps,
-                          workspace=ws)
+    ws = torch.zeros(native.groupnorm_workspace_bytes(n_img, HW) // 4 + 1, dtype=torch.float32, device=DEV)
+    for _ in range(2):   # twice through the same workspace: the arrival counters must come back to zero
+        out.fill_(float("nan"))
+        native.groupnorm_silu(out, x1, g, b, n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2, frames_per_stat=fps,
+                              workspace=ws)
     x = x1 if x2 is None else torch.cat([x1, x2], dim=1)
     xr = x.float().reshape(n_img // fps, fps * HW, C).permute(0, 2, 1)     # [stat, C, L]
     ref = F.group_norm(xr, 32, g.float(), b.float(), eps)
@@ -190,6 +192,23 @@ def linear_small(R=3, N=100, K=256):
     ref = F.silu(F.linear(F.silu(x + xa).float(), w.float(), b.float()).half().float())
     torch.cuda.synchronize()
     return _cmp(out, ref)
+
+
+def linear_small_grouped(R=2, dims=(320, 640, 64, 1280)):
+    """Several independent y_g = x[:, off_g:off_g+C_g] @ W_g.T + b_g in one launch."""
+    total = sum(dims)
+    x = _rand(R, total, seed=1)
+    out = torch.full((R, total), float("nan"), device=DEV, dtype=torch.float16)
+    groups, ref, off = [], [], 0
+    for i, c in enumerate(dims):
+        w, b = _rand(c, c, scale=c ** -0.5, seed=10 + i), (_rand(c, seed=30 + i) if i % 2 == 0 else None)
+        groups.append((w, b, off, off))
+        ref.append(F.linear(x[:, off:off + c].float(), w.float(), None if b is None else b.float()))
+        off += c
+    table = native.pack_small_groups(groups, DEV)
+    native.linear_small_grouped(out, x, table, n_groups=len(dims), max_n=max(dims))
+    torch.cuda.synchronize()
+    return _cmp(out, torch.cat(ref, dim=1))
 
 
 def sinusoid(dim=320):
@@ -306,6 +325,16 @@ ALL_CHECKS = {
     "groupnorm_temporal": lambda: groupnorm(n_img=6, HW=50, C1=320, fps=3, eps=1e-6, silu=False),
     "attn_temporal": lambda: attn_temporal(),
     "attn_temporal_25": lambda: attn_temporal(B=1, Fr=25, HW=9, heads=5),
+    "attn_temporal_25_many": lambda: attn_temporal(B=2, Fr=25, HW=2304, heads=10),
+    "attn_temporal_14": lambda: attn_temporal(B=1, Fr=14, HW=577, heads=5),
+    "attn_temporal_1": lambda: attn_temporal(B=2, Fr=1, HW=33, heads=1),
+    "attn_temporal_8": lambda: attn_temporal(B=1, Fr=8, HW=100, heads=3),
+    "attn_temporal_17": lambda: attn_temporal(B=1, Fr=17, HW=100, heads=2),
+    "attn_temporal_32": lambda: attn_temporal(B=1, Fr=32, HW=64, heads=20),
+    "linear_small_grouped": lambda: linear_small_grouped(),
+    "groupnorm_1280": lambda: groupnorm(n_img=3, HW=144, C1=1280, eps=1e-6),
+    "groupnorm_cat_1920": lambda: groupnorm(n_img=2, HW=576, C1=1280, C2=640),
+    "groupnorm_temporal_big": lambda: groupnorm(n_img=10, HW=2304, C1=640, fps=5),
     "dummy_unet": lambda: dummy_unet(),
     "simt_gemm_linear": lambda: gemm_linear(impl=1),
     "simt_gemm_split": lambda: gemm_linear(impl=1, K=384, split=True),

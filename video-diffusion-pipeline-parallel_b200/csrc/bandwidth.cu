@@ -39,6 +39,10 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 constexpr int GN_PIX_PER_CHUNK = 64;   // statistics pass (fixes the workspace layout); larger chunks measured slower
 constexpr int GN_APPLY_PIX = 64;       // apply pass
 constexpr int GN_GROUPS = 32;
+// The workspace starts with a fixed block of arrival counters (one per statistics group), so calls with
+// different (n_img, HW) that share one workspace never alias a counter with another call's partial sums.
+constexpr int GN_MAX_STATS = 4096;
+constexpr size_t GN_COUNTER_BYTES = GN_MAX_STATS * sizeof(unsigned);
 
 __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const __half* x2, int C2, long long pix,
                                                 int c0) {
@@ -48,8 +52,10 @@ __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const 
 // partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels
 __global__ void __launch_bounds__(512)
 gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
-                  float2* __restrict__ partial) {
+                  float2* partial, unsigned* counters, int frames_per_stat, float count, float eps,
+                  float2* __restrict__ stats) {
   extern __shared__ float2 red[];  // [rows][C]
+  __shared__ int s_last;
   const int C = C1 + C2;
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
@@ -92,40 +98,50 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
         b += v.y;
       }
     partial[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS + tid] = make_float2(a, b);
+    __threadfence();
   }
-}
-
-// stats[st][g] = (mean, rstd), st = image / frames_per_stat; 8 threads per group, fixed summation order
-__global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float2* __restrict__ partial, int n_chunks, int frames_per_stat, float count, float eps,
-                   float2* __restrict__ stats) {
-  __shared__ double sa[GN_GROUPS][8], sb[GN_GROUPS][8];
-  const int st = blockIdx.x;
-  const int g = threadIdx.x & 31;
-  const int part = threadIdx.x >> 5;
-  const int total = frames_per_stat * n_chunks;
-  const float2* base = partial + static_cast<long long>(st) * total * GN_GROUPS + g;
-  double a = 0.0, b = 0.0;
-  for (int i = part; i < total; i += 8) {
-    const float2 v = base[static_cast<long long>(i) * GN_GROUPS];
-    a += v.x;
-    b += v.y;
-  }
-  sa[g][part] = a;
-  sb[g][part] = b;
+  // The last block to finish for a statistics group (image, or frames_per_stat images) reduces that
+  // group's partials in a fixed order -> stats[st][g] = (mean, rstd).  No separate finalize launch; the
+  // counter is left at zero for the next call.
   __syncthreads();
-  if (part == 0) {
-    a = 0.0;
-    b = 0.0;
-    for (int i = 0; i < 8; ++i) {
-      a += sa[g][i];
-      b += sb[g][i];
+  const int st = n / frames_per_stat;
+  const int total = frames_per_stat * gridDim.x;
+  if (tid == 0) {
+    const unsigned old = atomicAdd(&counters[st], 1u);
+    s_last = old == static_cast<unsigned>(total - 1);
+    if (s_last) counters[st] = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nthreads = blockDim.x * blockDim.y;
+  const int parts = nthreads >> 5;  // >= 1: blocks have at least 32 threads
+  double* sa = reinterpret_cast<double*>(red);  // [parts][32] sums, then [parts][32] sums of squares
+  double* sb = sa + parts * GN_GROUPS;
+  const int g = tid & 31, part = tid >> 5;
+  if (part < parts) {
+    const float2* base = partial + static_cast<long long>(st) * total * GN_GROUPS + g;
+    double a = 0.0, b = 0.0;
+    for (int i = part; i < total; i += parts) {
+      const float2 v = __ldcg(base + static_cast<long long>(i) * GN_GROUPS);
+      a += v.x;
+      b += v.y;
+    }
+    sa[part * GN_GROUPS + g] = a;
+    sb[part * GN_GROUPS + g] = b;
+  }
+  __syncthreads();
+  if (tid < GN_GROUPS) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < parts; ++i) {
+      a += sa[i * GN_GROUPS + tid];
+      b += sb[i * GN_GROUPS + tid];
     }
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[st * GN_GROUPS + g] = make_float2(static_cast<float>(mean),
-                                            static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+    stats[st * GN_GROUPS + tid] = make_float2(static_cast<float>(mean),
+                                              static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
   }
 }
 
@@ -357,6 +373,55 @@ linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ x_a
   }
 }
 
+// Many independent small linears in one launch (the 1-token cross-attention output projections of all
+// 32 transformer blocks): group = blockIdx.y, y[r, y_off + n] = x[r, x_off : x_off + K] . W[n, :] + bias[n].
+struct SmallGroup {
+  const __half* W;     // [N, K], K contiguous
+  const __half* bias;  // [N] or null
+  int x_off, y_off, N, K;
+};
+static_assert(sizeof(SmallGroup) == sizeof(svdpp_small_group), "ABI struct mismatch");
+
+__global__ void __launch_bounds__(128)
+linear_small_grouped_kernel(const __half* __restrict__ x, long long ldx, const SmallGroup* __restrict__ groups,
+                            __half* __restrict__ y, long long ldy, int R) {
+  const SmallGroup gr = groups[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + warp;
+  if (n >= gr.N) return;
+  const __half* wr = gr.W + static_cast<long long>(n) * gr.K;
+  const __half* xg = x + gr.x_off;
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k8 = lane; k8 < (gr.K >> 3); k8 += 32) {
+      float w[8];
+      unpack8(*reinterpret_cast<const uint4*>(wr + 8 * k8), w);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r0 + r < R) {
+          float a[8];
+          unpack8(*reinterpret_cast<const uint4*>(xg + static_cast<long long>(r0 + r) * ldx + 8 * k8), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r] = fmaf(a[j], w[j], acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+    if (lane == 0) {
+      const float b = gr.bias ? __half2float(gr.bias[n]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r0 + r < R) y[static_cast<long long>(r0 + r) * ldy + gr.y_off + n] = __float2half_rn(acc[r] + b);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ sinusoid
 __global__ void sinusoid_kernel(const void* __restrict__ src, int src_kind, int src_mod, int n_vals, int dim,
                                 __half* __restrict__ out) {
@@ -561,7 +626,8 @@ using namespace svdpp;
 
 extern "C" size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW) {
   const size_t n_chunks = (static_cast<size_t>(HW) + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
-  return (static_cast<size_t>(n_img) * n_chunks * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
+  return GN_COUNTER_BYTES +
+         (static_cast<size_t>(n_img) * n_chunks * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
 }
 
 extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
@@ -577,8 +643,10 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   SVDPP_CHECK_ARG(frames_per_stat >= 1 && n_img % frames_per_stat == 0, "groupnorm: frames_per_stat=%d", frames_per_stat);
   SVDPP_CHECK_ARG(workspace_bytes >= svdpp_groupnorm_workspace_bytes(n_img, HW), "groupnorm: workspace too small");
   const int n_chunks = (HW + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
-  float2* partial = static_cast<float2*>(workspace);
+  unsigned* counters = static_cast<unsigned*>(workspace);
+  float2* partial = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + GN_COUNTER_BYTES);
   float2* stats = partial + static_cast<size_t>(n_img) * n_chunks * GN_GROUPS;
+  SVDPP_CHECK_ARG(n_img / frames_per_stat <= GN_MAX_STATS, "groupnorm: more than %d statistics groups", GN_MAX_STATS);
   const int nvc = C / 8;
   int rows = 256 / nvc;
   if (rows < 1) rows = 1;
@@ -592,13 +660,12 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
     configured = true;
   }
   SVDPP_CHECK_ARG(red_bytes <= 64 * 1024, "groupnorm: reduction buffer too large");
-  gn_partial_kernel<<<grid, block, red_bytes, stream>>>(static_cast<const __half*>(x1), C1,
-                                                        static_cast<const __half*>(x2), C2, HW, partial);
-  if (int e = check_launch("gn_partial_kernel")) return e;
-  const int n_stats = n_img / frames_per_stat;
   const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
-  gn_finalize_kernel<<<n_stats, 256, 0, stream>>>(partial, n_chunks, frames_per_stat, count, eps, stats);
-  if (int e = check_launch("gn_finalize_kernel")) return e;
+  SVDPP_CHECK_ARG(nvc * rows >= 32, "groupnorm: block too small");
+  gn_partial_kernel<<<grid, block, red_bytes, stream>>>(static_cast<const __half*>(x1), C1,
+                                                        static_cast<const __half*>(x2), C2, HW, partial, counters,
+                                                        frames_per_stat, count, eps, stats);
+  if (int e = check_launch("gn_partial_kernel")) return e;
   dim3 grid_apply((HW + GN_APPLY_PIX - 1) / GN_APPLY_PIX, n_img);
   gn_apply_kernel<<<grid_apply, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
@@ -644,6 +711,20 @@ extern "C" int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx,
                                                        static_cast<const __half*>(bias), static_cast<__half*>(y), ldy,
                                                        R, N, K, act_in, act_out);
   return check_launch("linear_small_kernel");
+}
+
+extern "C" int svdpp_linear_small_grouped(const void* x, int64_t ldx, const svdpp_small_group* groups_dev,
+                                          int32_t n_groups, int32_t max_n, void* y, int64_t ldy, int32_t R,
+                                          svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(x && groups_dev && y, "linear_small_grouped: null pointer");
+  SVDPP_CHECK_ARG(n_groups >= 1 && n_groups <= 65535 && max_n >= 1 && R >= 1, "linear_small_grouped: bad shape");
+  SVDPP_CHECK_ARG(ldx % 8 == 0, "linear_small_grouped: ldx must be a multiple of 8");
+  dim3 grid((max_n + 3) / 4, n_groups);
+  linear_small_grouped_kernel<<<grid, 128, 0, stream>>>(static_cast<const __half*>(x), ldx,
+                                                        reinterpret_cast<const SmallGroup*>(groups_dev),
+                                                        static_cast<__half*>(y), ldy, R);
+  return check_launch("linear_small_grouped_kernel");
 }
 
 extern "C" int svdpp_sinusoid_embed(const void* src, int32_t src_kind, int32_t src_mod, int32_t n_vals, int32_t dim,

@@ -7,8 +7,7 @@
 //   warp 4      TMA producer: Q once, then K_j / V_j blocks of 64 keys through 4-slot rings
 //   warp 5      TMEM allocator + MMA issuer: S_j = Q K_j^T (double buffered) and O += P_j V_j (V read
 //               MN-major straight from its row-major tile) into TMEM
-// svdpp_attn_temporal_f16: sequences of F <= 32 frames per (pixel, head): one warp each, CUDA cores
-//   (0.1 % of the UNet's FLOPs; bandwidth bound).
+// (svdpp_attn_temporal_f16, the F <= 32 frame attention, lives in attn_temporal.cu.)
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -310,130 +309,6 @@ __global__ void attn_spatial_simt_kernel(const __half* qkv, long long ld, AttnPa
   for (int i = 0; i < 64; ++i) dst[i] = __float2half_rn(o[i] / l);
 }
 
-// Temporal attention: warp per (batch, pixel, head); lane = frame.  K and V rows are converted to fp32 once
-// when staged in smem, so the two F x 64 inner products are pure LDS.128 + FFMA.
-constexpr int TATT_WARPS = 4;
-constexpr int TATT_PITCH = 68;  // floats per staged row (272 B, 16-byte aligned, spreads banks)
-__global__ void __launch_bounds__(128)
-attn_temporal_kernel(const __half* __restrict__ qkv, long long ld, int q_off, int k_off, int v_off,
-                     __half* __restrict__ out, long long ldo, int B, int F, int HW, int heads, float scale_log2) {
-  extern __shared__ __align__(16) float tsm[];  // [warps][2][32][PITCH]
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  float* sK = tsm + warp * 2 * 32 * TATT_PITCH;
-  float* sV = sK + 32 * TATT_PITCH;
-  const long long unit = static_cast<long long>(blockIdx.x) * TATT_WARPS + warp;
-  const long long total = static_cast<long long>(B) * HW * heads;
-  if (unit >= total) return;
-  const int head = static_cast<int>(unit % heads);
-  const long long bp = unit / heads;
-  const int pix = static_cast<int>(bp % HW);
-  const int b = static_cast<int>(bp / HW);
-  const bool active = lane < F;
-  const long long row = (static_cast<long long>(b) * F + (active ? lane : 0)) * HW + pix;
-  const __half* base = qkv + row * ld + head * 64;
-  float q[64];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(base + q_off);
-    const uint4* kp = reinterpret_cast<const uint4*>(base + k_off);
-    const uint4* vp = reinterpret_cast<const uint4*>(base + v_off);
-    uint4 qu[8], ku[8], vu[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {  // 24 independent 16-byte loads in flight per lane
-      qu[i] = qp[i];
-      ku[i] = kp[i];
-      vu[i] = vp[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const __half2* hq = reinterpret_cast<const __half2*>(&qu[i]);
-      const __half2* hk = reinterpret_cast<const __half2*>(&ku[i]);
-      const __half2* hv = reinterpret_cast<const __half2*>(&vu[i]);
-      float kf[8], vf[8];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 fq = __half22float2(hq[t]);
-        const float2 fk = __half22float2(hk[t]);
-        const float2 fv = __half22float2(hv[t]);
-        q[i * 8 + 2 * t] = fq.x * scale_log2;   // fold the softmax scale into q
-        q[i * 8 + 2 * t + 1] = fq.y * scale_log2;
-        kf[2 * t] = fk.x;
-        kf[2 * t + 1] = fk.y;
-        vf[2 * t] = fv.x;
-        vf[2 * t + 1] = fv.y;
-      }
-      if (active) {
-        float4* dk = reinterpret_cast<float4*>(sK + lane * TATT_PITCH + i * 8);
-        float4* dv = reinterpret_cast<float4*>(sV + lane * TATT_PITCH + i * 8);
-        dk[0] = make_float4(kf[0], kf[1], kf[2], kf[3]);
-        dk[1] = make_float4(kf[4], kf[5], kf[6], kf[7]);
-        dv[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
-        dv[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
-      }
-    }
-  }
-  __syncwarp();
-  float s[32];
-  float mx = -CUDART_INF_F;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    s[k] = -CUDART_INF_F;
-    if (k < F) {  // warp-uniform
-      float a4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float4* kr = reinterpret_cast<const float4*>(sK + k * TATT_PITCH);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 kk = kr[i];  // broadcast read
-        a4[0] = fmaf(q[4 * i], kk.x, a4[0]);
-        a4[1] = fmaf(q[4 * i + 1], kk.y, a4[1]);
-        a4[2] = fmaf(q[4 * i + 2], kk.z, a4[2]);
-        a4[3] = fmaf(q[4 * i + 3], kk.w, a4[3]);
-      }
-      const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-      s[k] = acc;
-      mx = fmaxf(mx, acc);
-    }
-  }
-  float l = 0.f;
-  float o[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) o[i] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    if (k < F) {
-      const float pr = fast_exp2(s[k] - mx);
-      l += pr;
-      const float prh = __half2float(__float2half_rn(pr));
-      const float4* vr = reinterpret_cast<const float4*>(sV + k * TATT_PITCH);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 vv = vr[i];
-        o[4 * i] = fmaf(prh, vv.x, o[4 * i]);
-        o[4 * i + 1] = fmaf(prh, vv.y, o[4 * i + 1]);
-        o[4 * i + 2] = fmaf(prh, vv.z, o[4 * i + 2]);
-        o[4 * i + 3] = fmaf(prh, vv.w, o[4 * i + 3]);
-      }
-    }
-  }
-  if (active) {
-    const float inv = 1.0f / l;
-    __half* dst = out + row * ldo + head * 64;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      __half2 h0 = __floats2half2_rn(o[i * 8 + 0] * inv, o[i * 8 + 1] * inv);
-      __half2 h1 = __floats2half2_rn(o[i * 8 + 2] * inv, o[i * 8 + 3] * inv);
-      __half2 h2 = __floats2half2_rn(o[i * 8 + 4] * inv, o[i * 8 + 5] * inv);
-      __half2 h3 = __floats2half2_rn(o[i * 8 + 6] * inv, o[i * 8 + 7] * inv);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2);
-      u.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(dst + i * 8) = u;
-    }
-  }
-}
-
 }  // namespace svdpp
 
 using namespace svdpp;
@@ -477,26 +352,4 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
   dim3 grid((d->S + 127) / 128, d->heads, d->n_img);
   attn_spatial_tc_kernel<<<grid, 192, ATT_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
   return check_launch("attn_spatial_tc_kernel");
-}
-
-extern "C" int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off,
-                                        void* out, int64_t ldo, int32_t B, int32_t F, int32_t HW, int32_t heads,
-                                        float scale, svdpp_stream stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SVDPP_CHECK_ARG(qkv && out, "attn_temporal: null pointers");
-  SVDPP_CHECK_ARG(F >= 1 && F <= 32, "attn_temporal: F=%d must be in [1,32]", F);
-  SVDPP_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
-                  "attn_temporal: pitches/offsets must be multiples of 8");
-  const long long units = static_cast<long long>(B) * HW * heads;
-  const unsigned blocks = static_cast<unsigned>((units + 3) / 4);
-  constexpr int tsm_bytes = TATT_WARPS * 2 * 32 * TATT_PITCH * sizeof(float);  // 69632
-  static bool configured_t = false;
-  if (!configured_t) {
-    SVDPP_CUDA(cudaFuncSetAttribute(attn_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm_bytes));
-    configured_t = true;
-  }
-  attn_temporal_kernel<<<blocks, 128, tsm_bytes, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off, v_off,
-                                                   static_cast<__half*>(out), ldo, B, F, HW, heads,
-                                                   scale * 1.4426950408889634f);
-  return check_launch("attn_temporal_kernel");
 }

@@ -193,6 +193,17 @@ class NativeUNet(nn.Module):
         self._temb_off += cout
         return off, cout
 
+    def _reg_cross(self, prefix: str) -> Tuple[int, int]:
+        """Cross-attention to the single CLIP token: register to_v / to_out.0 in the network-wide tables
+        (all to_v as one stacked weight, all to_out as one grouped launch); returns the column slice."""
+        wv = self._g(prefix + ".to_v.weight").contiguous()
+        wo, bo = self._small(prefix + ".to_out.0")
+        off, c = self._ca_off, wv.shape[0]
+        self._ca_wv.append(wv)
+        self._ca_groups.append((wo, bo, off, off))
+        self._ca_off += c
+        return off, c
+
     def _fuse_qkv(self, prefix: str) -> _Lin:
         w = torch.cat([self._g(prefix + ".to_q.weight"), self._g(prefix + ".to_k.weight"),
                        self._g(prefix + ".to_v.weight")], dim=0)
@@ -203,12 +214,12 @@ class NativeUNet(nn.Module):
         P["norm"], P["proj_in"] = self._norm(prefix + ".norm"), self._lin(prefix + ".proj_in")
         s, t = prefix + ".transformer_blocks.0", prefix + ".temporal_transformer_blocks.0"
         P["norm1"], P["qkv1"], P["out1"] = self._norm(s + ".norm1"), self._fuse_qkv(s + ".attn1"), self._lin(s + ".attn1.to_out.0")
-        P["ca_v"], P["ca_o"] = self._small(s + ".attn2.to_v", bias=False), self._small(s + ".attn2.to_out.0")
+        P["ca"] = self._reg_cross(s + ".attn2")
         P["norm3"], P["ff1"], P["ff2"] = self._norm(s + ".norm3"), self._geglu(s + ".ff.net.0.proj"), self._lin(s + ".ff.net.2")
         P["t_norm_in"], P["t_ffin1"], P["t_ffin2"] = (self._norm(t + ".norm_in"), self._geglu(t + ".ff_in.net.0.proj"),
                                                       self._lin(t + ".ff_in.net.2"))
         P["t_norm1"], P["t_qkv"], P["t_out1"] = self._norm(t + ".norm1"), self._fuse_qkv(t + ".attn1"), self._lin(t + ".attn1.to_out.0")
-        P["t_ca_v"], P["t_ca_o"] = self._small(t + ".attn2.to_v", bias=False), self._small(t + ".attn2.to_out.0")
+        P["t_ca"] = self._reg_cross(t + ".attn2")
         P["t_norm3"], P["t_ff1"], P["t_ff2"] = self._norm(t + ".norm3"), self._geglu(t + ".ff.net.0.proj"), self._lin(t + ".ff.net.2")
         P["pos1"], P["pos2"] = self._small(prefix + ".time_pos_embed.linear_1"), self._small(prefix + ".time_pos_embed.linear_2")
         P["alpha"] = self._alpha(prefix + ".time_mixer.mix_factor")
@@ -223,6 +234,7 @@ class NativeUNet(nn.Module):
         attn = tuple(cfg["down_attn"])
         L = cfg["layers_per_block"]
         self._temb_w, self._temb_b, self._temb_off = [], [], 0
+        self._ca_wv, self._ca_groups, self._ca_off = [], [], 0
         self.conv_in = self._conv3x3("conv_in")
         self.time_mlp = (self._small("time_embedding.linear_1"), self._small("time_embedding.linear_2"))
         self.add_mlp = (self._small("add_embedding.linear_1"), self._small("add_embedding.linear_2"))
@@ -257,6 +269,11 @@ class NativeUNet(nn.Module):
         self.temb_b = self._keep(torch.cat(self._temb_b, dim=0).contiguous())
         self.temb_total = self._temb_off
         del self._temb_w, self._temb_b
+        self.ca_wv = self._keep(torch.cat(self._ca_wv, dim=0).contiguous())     # [sum C, 1024]
+        self.ca_table = self._keep(native.pack_small_groups(self._ca_groups, self.device_))
+        self.ca_n_groups, self.ca_total = len(self._ca_groups), self._ca_off
+        self.ca_max_n = max(g[0].shape[0] for g in self._ca_groups)
+        del self._ca_wv, self._ca_groups
 
     def weight_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._tensors)
@@ -269,7 +286,8 @@ class NativeUNet(nn.Module):
         C = x1.shape[1] + (0 if x2 is None else x2.shape[1])
         need = native.groupnorm_workspace_bytes(n_img, HW)
         if self._gn_ws is None or self._gn_ws.numel() * 4 < need:
-            self._gn_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device_)
+            # zero-filled: the tail holds the arrival counters of the statistics kernel
+            self._gn_ws = torch.zeros((need + 3) // 4, dtype=torch.float32, device=self.device_)
         out = self._new(x1.shape[0], C)
         return native.groupnorm_silu(out, x1, norm[0], norm[1], n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2,
                                      frames_per_stat=fps, workspace=self._gn_ws)
@@ -330,15 +348,16 @@ class NativeUNet(nn.Module):
             self._pos_cache[key] = self._small_mlp(s, P["pos1"], P["pos2"])
         return self._pos_cache[key]
 
-    def _cross_vec(self, enc2d, v, o):
-        """Cross-attention with a single context token: softmax over one key is 1, so the block adds
-        to_out(to_v(ctx)) to every token (q/k projections and norm2 cannot influence the result)."""
-        h = self._new(enc2d.shape[0], v[0].shape[0])
-        native.linear_small(h, enc2d, v[0], None)
-        y = self._new(enc2d.shape[0], o[0].shape[0])
-        return native.linear_small(y, h, o[0], o[1])
+    def _cross_vecs(self, enc2d: torch.Tensor) -> torch.Tensor:
+        """Cross-attention with a single context token: softmax over one key is 1, so each block adds
+        to_out(to_v(ctx)) to every token (q/k projections and norm2 cannot influence the result).  All 32
+        blocks' vectors in two launches: stacked to_v, then the grouped to_out."""
+        h = self._new(enc2d.shape[0], self.ca_total)
+        native.linear_small(h, enc2d, self.ca_wv, None)
+        y = self._new(enc2d.shape[0], self.ca_total)
+        return native.linear_small_grouped(y, h, self.ca_table, n_groups=self.ca_n_groups, max_n=self.ca_max_n)
 
-    def _transformer(self, x, P, enc2d, B, F, H, W):
+    def _transformer(self, x, P, cvs, B, F, H, W):
         HW, n_img, M = H * W, B * F, x.shape[0]
         C, heads = x.shape[1], P["heads"]
         scale = 1.0 / math.sqrt(C // heads)
@@ -350,7 +369,8 @@ class NativeUNet(nn.Module):
         qkv = self._linear(n1, P["qkv1"])
         att = native.attn_spatial(self._new(M, C), qkv, n_img=n_img, S=HW, heads=heads, q_off=0, k_off=C,
                                   v_off=2 * C, scale=scale, impl=self.attn_impl)
-        cv = self._cross_vec(enc2d, P["ca_v"], P["ca_o"])
+        o_, c_ = P["ca"]
+        cv = cvs[:, o_:o_ + c_]
         h2 = self._linear(att, P["out1"], r1=h0, rowvec=cv, rv_hw=HW, rv_div=F)
         n3 = native.layernorm(self._new(M, C), h2, *P["norm3"])
         hs = self._linear(self._linear(n3, P["ff1"]), P["ff2"], r1=h2)
@@ -363,7 +383,8 @@ class NativeUNet(nn.Module):
         qkvt = self._linear(n1t, P["t_qkv"])
         attt = native.attn_temporal(self._new(M, C), qkvt, B=B, F=F, HW=HW, heads=heads, q_off=0, k_off=C,
                                     v_off=2 * C, scale=scale)
-        cvt = self._cross_vec(enc2d, P["t_ca_v"], P["t_ca_o"])
+        o_, c_ = P["t_ca"]
+        cvt = cvs[:, o_:o_ + c_]
         t2 = self._linear(attt, P["t_out1"], r1=t1, rowvec=cvt, rv_hw=HW, rv_div=F)
         n3t = native.layernorm(self._new(M, C), t2, *P["t_norm3"])
         # blend fused into the last temporal GEMM: a*hs + (1-a)*(ff + t2)
@@ -389,6 +410,7 @@ class NativeUNet(nn.Module):
         e_a = self._small_mlp(s_a.reshape(B, -1), *self.add_mlp)
         tembs = self._new(B, self.temb_total)   # every time_emb_proj(silu(emb)) of the network at once
         native.linear_small(tembs, e_t, self.temb_w, self.temb_b, x_add=e_a, act_in=1)
+        cvs = self._cross_vecs(enc2d)
         # --- conv_in (8 channels: gather the 3x3 windows, K padded 72 -> 128)
         cin = x_in.shape[1]
         cols = self._new(x_in.shape[0], self.conv_in.w.shape[1])
@@ -401,7 +423,7 @@ class NativeUNet(nn.Module):
             for j, R in enumerate(blk["res"]):
                 x = self._resblock(x, None, R, tembs, B, F, h, w)
                 if blk["attn"]:
-                    x = self._transformer(x, blk["attn"][j], enc2d, B, F, h, w)
+                    x = self._transformer(x, blk["attn"][j], cvs, B, F, h, w)
                 skips.append(x)
             if blk["down"] is not None:
                 C = x.shape[1]
@@ -412,13 +434,13 @@ class NativeUNet(nn.Module):
                 h, w = ho, wo
                 skips.append(x)
         x = self._resblock(x, None, self.mid["res"][0], tembs, B, F, h, w)
-        x = self._transformer(x, self.mid["attn"], enc2d, B, F, h, w)
+        x = self._transformer(x, self.mid["attn"], cvs, B, F, h, w)
         x = self._resblock(x, None, self.mid["res"][1], tembs, B, F, h, w)
         for blk in self.up:
             for j, R in enumerate(blk["res"]):
                 x = self._resblock(x, skips.pop(), R, tembs, B, F, h, w)
                 if blk["attn"]:
-                    x = self._transformer(x, blk["attn"][j], enc2d, B, F, h, w)
+                    x = self._transformer(x, blk["attn"][j], cvs, B, F, h, w)
             if blk["up"] is not None:
                 C = x.shape[1]
                 up = native.upsample2x(self._new(B * F * 4 * h * w, C), x, n_img=B * F, H=h, W=w, Cc=C)

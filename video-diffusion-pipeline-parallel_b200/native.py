@@ -20,7 +20,8 @@ GEMM_BN = 160  # N tile of the tcgen05 GEMM; weights are padded / GEGLU-interlea
 EXPORTED_SYMBOLS = (
     "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_gemm_f16",
     "svdpp_attn_spatial_f16", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
-    "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_sinusoid_embed",
+    "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_linear_small_grouped",
+    "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
     "svdpp_euler_vpred_step", "svdpp_dummy_unet_step",
 )
@@ -105,6 +106,8 @@ def load():
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     lib.svdpp_linear_small.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_linear_small_grouped.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                               C.c_int64, C.c_int32, C.c_void_p]
     lib.svdpp_sinusoid_embed.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p]
     lib.svdpp_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -286,6 +289,34 @@ def linear_small(out, x, w, bias=None, *, x_add=None, act_in=0, act_out=0) -> to
     _check(load().svdpp_linear_small(x.data_ptr(), _ptr(x_add), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
                                      out.data_ptr(), out.stride(0), R, N, K, act_in, act_out, _stream()),
            "svdpp_linear_small")
+    _count(1)
+    return out
+
+
+class SmallGroup(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("bias", C.c_void_p), ("x_off", C.c_int32), ("y_off", C.c_int32),
+                ("N", C.c_int32), ("K", C.c_int32)]
+
+
+def pack_small_groups(groups, device) -> torch.Tensor:
+    """[(W [N,K] contiguous, bias or None, x_off, y_off)] -> device table of ``svdpp_small_group``."""
+    arr = (SmallGroup * len(groups))()
+    for i, (w, b, x_off, y_off) in enumerate(groups):
+        _req(w)
+        if not w.is_contiguous() or x_off % 8 or w.shape[1] % 8:
+            raise NativeError("small group: W must be contiguous, K and x_off multiples of 8")
+        arr[i].W, arr[i].bias = w.data_ptr(), _ptr(b)
+        arr[i].x_off, arr[i].y_off, arr[i].N, arr[i].K = x_off, y_off, w.shape[0], w.shape[1]
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return raw.to(device)
+
+
+def linear_small_grouped(out, x, table: torch.Tensor, *, n_groups: int, max_n: int) -> torch.Tensor:
+    """All groups of ``table`` (see ``pack_small_groups``) in one launch; x: [R, *], out: [R, *]."""
+    _req(out), _req(x)
+    _check(load().svdpp_linear_small_grouped(x.data_ptr(), x.stride(0), table.data_ptr(), n_groups, max_n,
+                                             out.data_ptr(), out.stride(0), x.shape[0], _stream()),
+           "svdpp_linear_small_grouped")
     _count(1)
     return out
 
