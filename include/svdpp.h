@@ -96,7 +96,7 @@ int svdpp_attn_temporal_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t 
 /* GroupNorm(32 groups) [+ SiLU] over channels-last input that may be the channel concatenation
  * [x1 (C1) | x2 (C2)] (the up-block skip cat); statistics per (image, group), or per
  * (frames_per_stat consecutive images, group) for the temporal ResBlock's 5-D GroupNorm.
- * out is [n_img*HW, C1+C2].  workspace >= svdpp_groupnorm_workspace_bytes(), its first 16 KB ZERO-FILLED before the first
+ * out is [n_img*HW, C1+C2].  workspace >= svdpp_groupnorm_workspace_bytes(), its first 32 KB ZERO-FILLED before the first
  * use (it holds arrival counters that every call leaves at zero again).  Deterministic: fixed summation order.
  * Replaces: nn.GroupNorm + SiLU in ResnetBlock2D / TemporalResnetBlock / transformer norm / conv_norm_out. */
 size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW);

@@ -372,12 +372,18 @@ ALL_CHECKS = {
     "tc_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=0),
     "tc_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=0),
     "tc_attn_spatial_rescale": lambda: attn_spatial(n_img=2, S=1000, heads=2, impl=0, growing=True),
+    "tc2_attn_spatial_256": lambda: attn_spatial(n_img=1, S=256, heads=1, impl=2),
+    "tc2_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=2),
+    "tc2_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=2),
+    "tc2_attn_spatial_576": lambda: attn_spatial(n_img=2, S=576, heads=3, impl=2),
+    "tc2_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=2),
+    "tc2_attn_spatial_rescale": lambda: attn_spatial(n_img=2, S=1000, heads=2, impl=2, growing=True),
     "simt_attn_spatial_rescale": lambda: attn_spatial(n_img=1, S=600, heads=1, impl=1, growing=True),
 }
 
 
 # ------------------------------------------------------------------------------------------ whole UNet
-def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=0, seed=0):
+def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=None, seed=0):
     from oracle.unet_torch import UNetSpatioTemporalConditionModel, tiny_config
     from vdpp_b200.models.native_unet import NativeUNet
     cfg = tiny_config(**(cfg_over or {}))
@@ -387,7 +393,7 @@ def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=0, seed=0):
     return oracle, nat
 
 
-def unet_tiny(gemm_impl=0, attn_impl=0, B=1, Fr=3, H=16, W=16, cfg_over=None):
+def unet_tiny(gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, cfg_over=None):
     """NativeUNet vs the torch oracle (fp16 library kernels) and vs the oracle in fp32, same weights."""
     oracle, nat = _tiny_pair(cfg_over, gemm_impl, attn_impl)
     g = torch.Generator(device=DEV)
@@ -411,7 +417,7 @@ def unet_tiny(gemm_impl=0, attn_impl=0, B=1, Fr=3, H=16, W=16, cfg_over=None):
     return r
 
 
-def svd_steps(n_steps=4, total=25, cfg_scale=None, gemm_impl=0, attn_impl=0, B=1, Fr=3, H=16, W=16, graph=False):
+def svd_steps(n_steps=4, total=25, cfg_scale=None, gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, graph=False):
     """StableVideoUNet (native) vs the oracle restatement of the reference wrapper, a few Euler steps."""
     from oracle.svd_step import OracleStep, dummy_conditioning
     from vdpp_b200.models import StableVideoUNet
@@ -447,6 +453,7 @@ UNET_CHECKS = {
     "unet_tiny_tc_b2": lambda: unet_tiny(0, 0, B=2, Fr=2, H=16, W=32),
     "unet_tiny_pair": lambda: unet_tiny(2, 0),
     "unet_tiny_pair256": lambda: unet_tiny(3, 0, cfg_over=dict(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))),
+    "unet_tiny_tc_fmha2": lambda: unet_tiny(0, 2),
     "svd_steps_simt": lambda: svd_steps(gemm_impl=1, attn_impl=1),
     "svd_steps_tc": lambda: svd_steps(),
     "svd_steps_tc_cfg": lambda: svd_steps(cfg_scale=3.0),

@@ -16,6 +16,7 @@ ap.add_argument("--S", type=int, default=9216)
 ap.add_argument("--heads", type=int, default=5)
 ap.add_argument("--imgs", type=int, default=25)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--impl", type=int, default=0)
 a = ap.parse_args()
 C = a.heads * 64
 M = a.imgs * a.S
@@ -26,9 +27,9 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 best = 1e9
 for _ in range(a.iters):
     e0.record()
-    native.attn_spatial(out, qkv, n_img=a.imgs, S=a.S, heads=a.heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125)
+    native.attn_spatial(out, qkv, n_img=a.imgs, S=a.S, heads=a.heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125, impl=a.impl)
     e1.record()
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 fl = 4.0 * a.S * a.S * 64 * a.heads * a.imgs
-print(f"attn_spatial S={a.S} heads={a.heads} imgs={a.imgs}: {best:.3f} ms  {fl / best / 1e9:.1f} TFLOP/s  finite={bool(torch.isfinite(out).all())}")
+print(f"attn_spatial impl={a.impl} S={a.S} heads={a.heads} imgs={a.imgs}: {best:.3f} ms  {fl / best / 1e9:.1f} TFLOP/s  finite={bool(torch.isfinite(out).all())}")

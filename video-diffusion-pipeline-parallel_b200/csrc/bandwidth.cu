@@ -36,23 +36,26 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // owns the 8 channels [8*tx, 8*tx+8) and walks the pixels ty, ty+rows, ... of a 64-pixel chunk, so
 // consecutive threads touch consecutive 16-byte vectors (also across pixel boundaries) and per-channel
 // quantities (running sums, or scale/shift) live in registers.  grid = (chunks, images).
-constexpr int GN_PIX_PER_CHUNK = 64;   // statistics pass (fixes the workspace layout); larger chunks measured slower
-constexpr int GN_APPLY_PIX = 64;       // apply pass
+constexpr int GN_MAX_PIX = 64;         // pixels per block at high resolution; halved (down to 8) until the grid
+constexpr int GN_MIN_PIX = 8;          // has >= 4 blocks per SM (low-resolution levels: 144 pixels x 1280 channels)
 constexpr int GN_GROUPS = 32;
-// The workspace starts with a fixed block of arrival counters (one per statistics group), so calls with
-// different (n_img, HW) that share one workspace never alias a counter with another call's partial sums.
+// The workspace starts with a fixed block of arrival counters (per image, then per statistics group), so calls
+// with different (n_img, HW) that share one workspace never alias a counter with another call's partial sums.
 constexpr int GN_MAX_STATS = 4096;
-constexpr size_t GN_COUNTER_BYTES = GN_MAX_STATS * sizeof(unsigned);
+constexpr size_t GN_COUNTER_BYTES = 2 * GN_MAX_STATS * sizeof(unsigned);
 
 __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const __half* x2, int C2, long long pix,
                                                 int c0) {
   return c0 < C1 ? x1 + pix * C1 + c0 : x2 + pix * C2 + (c0 - C1);
 }
 
-// partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels
+// partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels.  The last block to finish
+// an image reduces that image's chunks (fixed order, fp64); for the temporal GroupNorm (statistics over
+// frames_per_stat images) the last image to finish reduces the per-image sums.  -> stats[st][g] = (mean, rstd).
+// No separate finalize launch; every counter is left at zero for the next call.
 __global__ void __launch_bounds__(512)
-gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
-                  float2* partial, unsigned* counters, int frames_per_stat, float count, float eps,
+gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int pix,
+                  float2* partial, double2* imgsum, unsigned* counters, int frames_per_stat, float count, float eps,
                   float2* __restrict__ stats) {
   extern __shared__ float2 red[];  // [rows][C]
   __shared__ int s_last;
@@ -60,8 +63,8 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * GN_PIX_PER_CHUNK;
-  const int p1 = min(p0 + GN_PIX_PER_CHUNK, HW);
+  const int p0 = blockIdx.x * pix;
+  const int p1 = min(p0 + pix, HW);
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
@@ -88,6 +91,7 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
   for (int j = 0; j < 8; ++j) red[threadIdx.y * C + c0 + j] = make_float2(s[j], ss[j]);
   __syncthreads();
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int n_chunks = gridDim.x;
   if (tid < GN_GROUPS) {
     const int cpg = C / GN_GROUPS;
     float a = 0.f, b = 0.f;
@@ -97,19 +101,14 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
         a += v.x;
         b += v.y;
       }
-    partial[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS + tid] = make_float2(a, b);
+    partial[(static_cast<long long>(n) * n_chunks + blockIdx.x) * GN_GROUPS + tid] = make_float2(a, b);
     __threadfence();
   }
-  // The last block to finish for a statistics group (image, or frames_per_stat images) reduces that
-  // group's partials in a fixed order -> stats[st][g] = (mean, rstd).  No separate finalize launch; the
-  // counter is left at zero for the next call.
   __syncthreads();
-  const int st = n / frames_per_stat;
-  const int total = frames_per_stat * gridDim.x;
   if (tid == 0) {
-    const unsigned old = atomicAdd(&counters[st], 1u);
-    s_last = old == static_cast<unsigned>(total - 1);
-    if (s_last) counters[st] = 0u;
+    const unsigned old = atomicAdd(&counters[n], 1u);
+    s_last = old == static_cast<unsigned>(n_chunks - 1);
+    if (s_last) counters[n] = 0u;
   }
   __syncthreads();
   if (!s_last) return;
@@ -120,9 +119,9 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
   double* sb = sa + parts * GN_GROUPS;
   const int g = tid & 31, part = tid >> 5;
   if (part < parts) {
-    const float2* base = partial + static_cast<long long>(st) * total * GN_GROUPS + g;
+    const float2* base = partial + static_cast<long long>(n) * n_chunks * GN_GROUPS + g;
     double a = 0.0, b = 0.0;
-    for (int i = part; i < total; i += parts) {
+    for (int i = part; i < n_chunks; i += parts) {
       const float2 v = __ldcg(base + static_cast<long long>(i) * GN_GROUPS);
       a += v.x;
       b += v.y;
@@ -131,12 +130,39 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
     sb[part * GN_GROUPS + g] = b;
   }
   __syncthreads();
+  double a = 0.0, b = 0.0;
   if (tid < GN_GROUPS) {
-    double a = 0.0, b = 0.0;
     for (int i = 0; i < parts; ++i) {
       a += sa[i * GN_GROUPS + tid];
       b += sb[i * GN_GROUPS + tid];
     }
+  }
+  const int st = n / frames_per_stat;
+  if (frames_per_stat > 1) {
+    if (tid < GN_GROUPS) {
+      imgsum[n * GN_GROUPS + tid] = make_double2(a, b);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned old = atomicAdd(&counters[GN_MAX_STATS + st], 1u);
+      s_last = old == static_cast<unsigned>(frames_per_stat - 1);
+      if (s_last) counters[GN_MAX_STATS + st] = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < GN_GROUPS) {
+      a = 0.0;
+      b = 0.0;
+      for (int f = 0; f < frames_per_stat; ++f) {
+        const double2 v = __ldcg(imgsum + (static_cast<long long>(st) * frames_per_stat + f) * GN_GROUPS + tid);
+        a += v.x;
+        b += v.y;
+      }
+    }
+  }
+  if (tid < GN_GROUPS) {
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -148,13 +174,13 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, const float2* __restrict__ stats,
-                __half* __restrict__ out, int HW, int frames_per_stat, int silu) {
+                __half* __restrict__ out, int HW, int pix, int frames_per_stat, int silu) {
   const int C = C1 + C2;
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * GN_APPLY_PIX;
-  const int p1 = min(p0 + GN_APPLY_PIX, HW);
+  const int p0 = blockIdx.x * pix;
+  const int p1 = min(p0 + pix, HW);
   const int cpg = C / GN_GROUPS;
   const float2* st = stats + (n / frames_per_stat) * GN_GROUPS;
   float sc[8], sh[8];
@@ -624,9 +650,15 @@ static inline unsigned grid_for(long long n, int threads, int max_blocks = 148 *
 
 using namespace svdpp;
 
+static int gn_pixels_per_block(int n_img, int HW) {
+  int pix = GN_MAX_PIX;
+  while (pix > GN_MIN_PIX && static_cast<long long>(n_img) * ((HW + pix - 1) / pix) < 4LL * num_sms()) pix >>= 1;
+  return pix;
+}
+
 extern "C" size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW) {
-  const size_t n_chunks = (static_cast<size_t>(HW) + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
-  return GN_COUNTER_BYTES +
+  const size_t n_chunks = (static_cast<size_t>(HW) + GN_MIN_PIX - 1) / GN_MIN_PIX;  // worst case (smallest blocks)
+  return GN_COUNTER_BYTES + static_cast<size_t>(n_img) * GN_GROUPS * sizeof(double2) +
          (static_cast<size_t>(n_img) * n_chunks * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
 }
 
@@ -642,15 +674,18 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   SVDPP_CHECK_ARG(C / 8 <= 512, "groupnorm: C=%d too large", C);
   SVDPP_CHECK_ARG(frames_per_stat >= 1 && n_img % frames_per_stat == 0, "groupnorm: frames_per_stat=%d", frames_per_stat);
   SVDPP_CHECK_ARG(workspace_bytes >= svdpp_groupnorm_workspace_bytes(n_img, HW), "groupnorm: workspace too small");
-  const int n_chunks = (HW + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
+  SVDPP_CHECK_ARG(n_img <= GN_MAX_STATS, "groupnorm: more than %d images", GN_MAX_STATS);
+  const int pix = gn_pixels_per_block(n_img, HW);
+  const int n_chunks = (HW + pix - 1) / pix;
   unsigned* counters = static_cast<unsigned*>(workspace);
-  float2* partial = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + GN_COUNTER_BYTES);
+  double2* imgsum = reinterpret_cast<double2*>(static_cast<uint8_t*>(workspace) + GN_COUNTER_BYTES);
+  float2* partial = reinterpret_cast<float2*>(imgsum + static_cast<size_t>(n_img) * GN_GROUPS);
   float2* stats = partial + static_cast<size_t>(n_img) * n_chunks * GN_GROUPS;
-  SVDPP_CHECK_ARG(n_img / frames_per_stat <= GN_MAX_STATS, "groupnorm: more than %d statistics groups", GN_MAX_STATS);
   const int nvc = C / 8;
   int rows = 256 / nvc;
   if (rows < 1) rows = 1;
-  if (rows > GN_PIX_PER_CHUNK) rows = GN_PIX_PER_CHUNK;
+  if (rows > pix) rows = pix;
+  while (nvc * rows < 32) ++rows;  // the in-kernel reductions need at least one full warp
   dim3 block(nvc, rows);
   dim3 grid(n_chunks, n_img);
   const size_t red_bytes = static_cast<size_t>(rows) * C * sizeof(float2);
@@ -661,15 +696,13 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   }
   SVDPP_CHECK_ARG(red_bytes <= 64 * 1024, "groupnorm: reduction buffer too large");
   const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
-  SVDPP_CHECK_ARG(nvc * rows >= 32, "groupnorm: block too small");
   gn_partial_kernel<<<grid, block, red_bytes, stream>>>(static_cast<const __half*>(x1), C1,
-                                                        static_cast<const __half*>(x2), C2, HW, partial, counters,
-                                                        frames_per_stat, count, eps, stats);
+                                                        static_cast<const __half*>(x2), C2, HW, pix, partial, imgsum,
+                                                        counters, frames_per_stat, count, eps, stats);
   if (int e = check_launch("gn_partial_kernel")) return e;
-  dim3 grid_apply((HW + GN_APPLY_PIX - 1) / GN_APPLY_PIX, n_img);
-  gn_apply_kernel<<<grid_apply, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
+  gn_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                              stats, static_cast<__half*>(out), HW, frames_per_stat, apply_silu);
+                                              stats, static_cast<__half*>(out), HW, pix, frames_per_stat, apply_silu);
   return check_launch("gn_apply_kernel");
 }
 

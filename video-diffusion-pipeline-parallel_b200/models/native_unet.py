@@ -99,7 +99,8 @@ def window_path_ok(W: int, C: int) -> bool:
 
 class NativeUNet(nn.Module):
     def __init__(self, state_dict: Mapping[str, torch.Tensor], config: Optional[dict] = None,
-                 device: torch.device | str = "cuda", gemm_impl: Optional[int] = None, attn_impl: int = 0):
+                 device: torch.device | str = "cuda", gemm_impl: Optional[int] = None,
+                 attn_impl: Optional[int] = None):
         super().__init__()
         self.cfg = dict(SVD_CONFIG)
         if config:
@@ -111,6 +112,8 @@ class NativeUNet(nn.Module):
         # 0: one CTA per 128x160 tile; 2: CTA pairs (cta_group::2), 256x160; 3: CTA pairs with 256x256 tiles where
         # N % 256 == 0 and the one-CTA kernel elsewhere; SVDPP_GEMM_IMPL overrides the default for experiments
         self.gemm_impl = int(os.environ.get("SVDPP_GEMM_IMPL", "3")) if gemm_impl is None else gemm_impl
+        # None: the two-tile FMHA (impl 2, P in TMEM) for long sequences, where its one CTA per SM amortises the
+        # prologue, and the 2-CTAs-per-SM kernel (impl 0) for S < 1024; an int forces one kernel (1 = CUDA cores)
         self.attn_impl = attn_impl
         self.dtype = torch.float16
         self._sd = state_dict
@@ -368,7 +371,8 @@ class NativeUNet(nn.Module):
         n1 = native.layernorm(self._new(M, C), h0, *P["norm1"])
         qkv = self._linear(n1, P["qkv1"])
         att = native.attn_spatial(self._new(M, C), qkv, n_img=n_img, S=HW, heads=heads, q_off=0, k_off=C,
-                                  v_off=2 * C, scale=scale, impl=self.attn_impl)
+                                  v_off=2 * C, scale=scale,
+                                  impl=(2 if HW >= 1024 else 0) if self.attn_impl is None else self.attn_impl)
         o_, c_ = P["ca"]
         cv = cvs[:, o_:o_ + c_]
         h2 = self._linear(att, P["out1"], r1=h0, rowvec=cv, rv_hw=HW, rv_div=F)
