@@ -128,6 +128,26 @@ def reference_arm(args) -> None:
     }))
 
 
+def cpu_dummy_simulator(total_steps: int = 25):
+    """The reference's CPU simulator workload (BASELINE config 1): DummyUNet(channels=4), latent [1,4,14,64,64]
+    fp32, `total_steps` steps on the host cores in one process (torch CPU kernels, as the reference runs it)."""
+    import torch
+    from vdpp_b200.models import DummyUNet
+    torch.manual_seed(1234)
+    model = DummyUNet(channels=4).eval()
+    torch.manual_seed(42)
+    lat = torch.randn(1, 4, 14, 64, 64)
+    with torch.no_grad():
+        lat = model(lat, 0)          # warm-up
+        t0 = time.perf_counter()
+        for step in range(total_steps):
+            lat = model(lat, step)
+        sec = time.perf_counter() - t0
+    return {"workload": f"DummyUNet(channels=4) latent 1x4x14x64x64 fp32, {total_steps} steps, 1 process",
+            "ms_per_step": 1000.0 * sec / total_steps, "videos_per_min": 60.0 / sec, "cores": torch.get_num_threads(),
+            "finite": bool(torch.isfinite(lat).all())}
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -376,10 +396,18 @@ def main() -> None:
         if peak is None:
             peak, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the same kernel family, from the committed ncu pass (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")))
+            if F_ == 25 and (H, W) == (72, 128) and not args.guidance_scale:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_gemm_dram_traffic.json (" + tj["source"] + ")"
+        except Exception:  # noqa: BLE001
+            pass
         result["roofline"] = {
-            "kernel": "gemm_tc_kernel<160,*> (tcgen05 GEMM + implicit-GEMM conv, all launches of one UNet forward)",
+            "kernel": "gemm_tc_kernel<160|256|128,*> (tcgen05 GEMM + implicit-GEMM conv, all launches of one UNet forward)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
             "algorithmic_tflop_per_forward": gemm_flops / 1e12,
         }
@@ -390,6 +418,15 @@ def main() -> None:
                 "achieved": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
                 "frac": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12 / peak, "launches": att[2], "ms": att[0]}
         result["kernel_ms_per_forward"] = {k: round(v[0], 3) for k, v in agg.items()}
+        if F_ == 25 and (H, W) == (72, 128):
+            try:   # achieved HBM GB/s of the bandwidth kernels at this workload's level-0 shapes (tools/bw_bench.py)
+                from tools.bw_bench import run_cases
+                del x
+                torch.cuda.empty_cache()
+                result["roofline_bandwidth"] = run_cases(F_, ["L0 C=320 per-image", "L0 C=320 per-video", "layernorm L0",
+                                                              "attn_temporal L0", "euler_vpred (no CFG)"], quiet=True)
+            except Exception as e:  # noqa: BLE001
+                result["roofline_bandwidth"] = {"error": f"{type(e).__name__}: {e}"}
         result["whole_step_tflops"] = (fl["total"] / 1e12) / (ms_total / 1000.0 / (n_videos * T / world)) if world == 1 else None
 
     # ---- CPU baseline (oracle port on the host cores), rank 0 at N=1 only
@@ -401,6 +438,7 @@ def main() -> None:
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"1 denoising step of the oracle (torch fp32, CPU) at {args.cpu_sample_frames} of {F_} frames, "
                           f"full {H}x{W} latent, scaled by frames x {T} steps; {sec:.2f} s measured"}
+            result["cpu_baseline"]["reference_simulator"] = cpu_dummy_simulator(T)
         except Exception as e:  # noqa: BLE001
             result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                       "sample": f"failed: {type(e).__name__}: {e}"}

@@ -56,7 +56,11 @@ def main():
     ap.add_argument("--frames", type=int, default=25)
     ap.add_argument("filters", nargs="*")
     args = ap.parse_args()
-    F_ = args.frames
+    run_cases(args.frames, args.filters)
+
+
+def run_cases(F_, filters=(), quiet=False):
+    """Time every case whose name contains one of `filters` (all if empty); returns the records."""
     H, W = 72, 128
     levels = [(H * W, 320, 5), (H * W // 4, 640, 10), (H * W // 16, 1280, 20), (H * W // 64, 1280, 20)]
     peak, peak_src = peak_gbs()
@@ -144,9 +148,10 @@ def main():
 
     out_path = os.path.join(ROOT, "gpurun_out", "bw_bench.jsonl")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    records = []
     with open(out_path, "a") as log:
         for name, mk, run, set_bytes, alg_bytes, note in cases:
-            if args.filters and not any(f in name for f in args.filters):
+            if filters and not any(f in name for f in filters):
                 continue
             ms = timed(mk, run, set_bytes)
             gbs = alg_bytes / (ms * 1e-3) / 1e9
@@ -154,9 +159,12 @@ def main():
                    "achieved_GBs": round(gbs, 1), "peak_GBs": peak, "frac": round(gbs / peak, 3), "peak_source": peak_src,
                    "variant": os.environ.get("SVDPP_TA_VARIANT", ""), "note": note}
             line = json.dumps(rec)
-            print(line, flush=True)
+            records.append(rec)
+            if not quiet:
+                print(line, flush=True)
             log.write(line + "\n")
             torch.cuda.empty_cache()
+    return records
 
 
 if __name__ == "__main__":

@@ -613,7 +613,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SVDPP_CHECK_ARG(d != nullptr, "gemm: null descriptor");
   // impl 3: CTA pairs with 256-wide tiles (N must be a multiple of 256; GEGLU weights interleaved per 128)
-  const int BN = impl == 3 ? 256 : 160;
+  // impl 4: one CTA per 128x128 tile (N a multiple of 128; no GEGLU) - for small M, where 128x128 tiles fill the
+  //         148 SMs' last wave better than 128x160 or 256x256
+  const int BN = impl == 3 ? 256 : (impl == 4 ? 128 : 160);
   SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
   SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
   SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
@@ -692,8 +694,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
     return check_launch("gemm_simt_kernel");
   }
-  SVDPP_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "gemm: unknown impl %d", impl);
-  const bool two = impl >= 2;  // CTA pairs (cta_group::2)
+  SVDPP_CHECK_ARG(impl == 0 || impl == 2 || impl == 3 || impl == 4, "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(!(impl == 4 && d->geglu), "gemm: impl 4 has no GEGLU epilogue");
+  const bool two = impl == 2 || impl == 3;  // CTA pairs (cta_group::2)
 
   CUtensorMap tmA, tmA2, tmB;
   if (!d->conv) {
@@ -739,6 +742,7 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     uint32_t box[2] = {64, static_cast<uint32_t>(two ? BN / 2 : BN)};
     if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
   }
+  if (impl == 4) return launch_tc<128, false, false>(tmA, tmA2, tmB, p, stream);
   if (impl == 3) {
     if (d->geglu) return launch_tc<256, true, true>(tmA, tmA2, tmB, p, stream);
     return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);

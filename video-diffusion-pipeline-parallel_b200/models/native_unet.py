@@ -120,6 +120,7 @@ class NativeUNet(nn.Module):
         self._tensors: List[torch.Tensor] = []   # keeps packed weights alive / counted
         self._pos_cache: Dict[Tuple[str, int], torch.Tensor] = {}
         self._gn_ws: Optional[torch.Tensor] = None
+        self._sms: Optional[int] = None
         self._build()
         self._sd = None
 
@@ -295,18 +296,37 @@ class NativeUNet(nn.Module):
         return native.groupnorm_silu(out, x1, norm[0], norm[1], n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2,
                                      frames_per_stat=fps, workspace=self._gn_ws)
 
-    def _impl(self, lin: _Lin) -> int:
+    # relative per-SM throughput of the tile shapes on large problems (measured: 256x256 CTA pairs +15-25 % over
+    # 128x160; 128x128 a little below it)
+    _TILE_SPEED = {3: 1.2, 0: 1.0, 4: 0.92}
+
+    def _impl(self, lin: _Lin, M: int = 1 << 30) -> int:
+        """Tile shape for one GEMM: the packed layout fixes it for GEGLU; otherwise, in auto mode (3), the
+        candidate whose last wave over the 148 SMs wastes least (matters at M = 3600, the 9x16 level)."""
         if lin.impl is not None:
             return lin.impl
-        if self.gemm_impl == 3:
-            return 3 if lin.w.shape[0] % 256 == 0 else 0
-        return self.gemm_impl
+        if self.gemm_impl != 3:
+            return self.gemm_impl
+        N = lin.w.shape[0]
+        sms = native.device_info()[2] if self._sms is None else self._sms
+        self._sms = sms
+        mt = (M + 127) // 128
+        best, best_t = 0, None
+        for impl, bn, per_cta in ((3, 256, 128 * 256), (0, 160, 128 * 160), (4, 128, 128 * 128)):
+            if N % bn or (impl == 4 and os.environ.get("SVDPP_NO_BN128")):
+                continue
+            work = ((mt + 1) // 2) * (N // bn) if impl == 3 else mt * (N // bn)
+            slots = sms // 2 if impl == 3 else sms
+            t = -(-work // slots) * per_cta / self._TILE_SPEED[impl]
+            if best_t is None or t < best_t:
+                best, best_t = impl, t
+        return best
 
     def _linear(self, a, lin: _Lin, *, a2=None, **epi):
         n_out = lin.n
         out = self._new(a.shape[0], n_out)
         return native.gemm(out, a, lin.w, bias=lin.b, a2=a2, geglu=lin.geglu, n_store=n_out,
-                           impl=self._impl(lin), **epi)
+                           impl=self._impl(lin, a.shape[0]), **epi)
 
     def _conv(self, a, lin: _Lin, dims, taps, **epi):
         B, F, H, W, C = dims
@@ -314,10 +334,10 @@ class NativeUNet(nn.Module):
         out = self._new(M, lin.n)
         if window_path_ok(W, C):
             return native.gemm(out, a, lin.w, bias=lin.b, conv_dims=dims, taps=taps, n_store=lin.n,
-                               impl=self._impl(lin), **epi)
+                               impl=self._impl(lin, M), **epi)
         cols = self._new(M, len(taps) * C)
         native.im2col(cols, a, B=B, F=F, H=H, W=W, Cc=C, Ho=H, Wo=W, stride=1, taps=taps)
-        return native.gemm(out, cols, lin.w, bias=lin.b, n_store=lin.n, impl=self._impl(lin), **epi)
+        return native.gemm(out, cols, lin.w, bias=lin.b, n_store=lin.n, impl=self._impl(lin, M), **epi)
 
     def _small_mlp(self, x, l1, l2, x_add=None):
         h = self._new(x.shape[0], l1[0].shape[0])
@@ -420,7 +440,7 @@ class NativeUNet(nn.Module):
         cols = self._new(x_in.shape[0], self.conv_in.w.shape[1])
         native.im2col(cols, x_in, B=B, F=F, H=H, W=W, Cc=cin, Ho=H, Wo=W, stride=1, taps=TAPS_3X3)
         x = native.gemm(self._new(x_in.shape[0], self.conv_in.n), cols, self.conv_in.w, bias=self.conv_in.b,
-                        n_store=self.conv_in.n, impl=self._impl(self.conv_in))
+                        n_store=self.conv_in.n, impl=self._impl(self.conv_in, x_in.shape[0]))
         skips = [x]
         h, w = H, W
         for blk in self.down:
