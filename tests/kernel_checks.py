@@ -384,6 +384,12 @@ ALL_CHECKS = {
     "tc2_attn_spatial_576": lambda: attn_spatial(n_img=2, S=576, heads=3, impl=2),
     "tc2_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=2),
     "tc2_attn_spatial_rescale": lambda: attn_spatial(n_img=2, S=1000, heads=2, impl=2, growing=True),
+    "tc3_attn_spatial_256": lambda: attn_spatial(n_img=1, S=256, heads=1, impl=3),
+    "tc3_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=3),
+    "tc3_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=3),
+    "tc3_attn_spatial_576": lambda: attn_spatial(n_img=2, S=576, heads=3, impl=3),
+    "tc3_attn_spatial_2304": lambda: attn_spatial(n_img=2, S=2304, heads=5, impl=3),
+    "tc3_attn_spatial_rescale": lambda: attn_spatial(n_img=2, S=1000, heads=2, impl=3, growing=True),
     "simt_attn_spatial_rescale": lambda: attn_spatial(n_img=1, S=600, heads=1, impl=1, growing=True),
 }
 

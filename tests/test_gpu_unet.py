@@ -74,3 +74,32 @@ def test_full_size_step_properties():
     model(x, 0)
     replay = model(x, 0)
     assert torch.equal(replay, eager)
+
+
+def test_safetensors_checkpoint_roundtrip(tmp_path):
+    """a diffusers-layout checkpoint directory (unet/*.safetensors with the
+    UNetSpatioTemporalConditionModel key names) loads through StableVideoUNet.from_pretrained into the native
+    weight arena and gives bit-identical steps to the same state dict passed in memory."""
+    from safetensors.torch import save_file
+    from vdpp_b200.models import StableVideoUNet
+    from vdpp_b200.models.native_unet import NativeUNet
+    oracle, nat = kc._tiny_pair()
+    (tmp_path / "unet").mkdir()
+    sd = {k: v.detach().half().contiguous().cpu() for k, v in oracle.state_dict().items()}
+    save_file(sd, str(tmp_path / "unet" / "diffusion_pytorch_model.fp16.safetensors"))
+    dev = torch.device("cuda")
+    loaded = StableVideoUNet.from_pretrained(str(tmp_path), config=oracle.config, device=dev)
+    assert isinstance(loaded.unet, NativeUNet)
+    direct = StableVideoUNet(unet=nat, timesteps=StableVideoUNet._default_timestep_schedule(25)).to(dev)
+    outs = []
+    for model in (loaded, direct):
+        torch.manual_seed(7)
+        model.set_dummy_conditioning(1, 3, 16, 16, dev)
+        torch.manual_seed(8)
+        x = torch.randn(1, 4, 3, 16, 16, device=dev).half() * model.init_noise_sigma
+        for s in range(2):
+            x = model(x, s)
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(FileNotFoundError):
+        StableVideoUNet.from_pretrained("stabilityai/stable-video-diffusion-img2vid-xt", device=dev)

@@ -36,8 +36,20 @@ constexpr int A2_BK = 128;                    // keys per block
 constexpr int A2_Q_BYTES = A2_BQ * 64 * 2;    // 16 KB
 constexpr int A2_KV_BYTES = A2_BK * 64 * 2;   // 16 KB
 constexpr int A2_STAGES = 3;
-constexpr int A2_SMEM_BYTES = 2 * A2_Q_BYTES + 2 * A2_STAGES * A2_KV_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int A2_THREADS = 352;
+constexpr int A2_SMEM_BYTES = 2 * A2_Q_BYTES + 2 * A2_STAGES * A2_KV_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                              2 * 2 * 2 * 128 * 4 /*row-max exchange*/;
+// SPLIT = threads per query row: 1 -> 8 softmax warps (thread = row, 128 columns), 2 -> 16 softmax warps (two
+// threads per row, 64 columns each, row maximum exchanged through smem + a 64-thread named barrier): four
+// instead of two softmax warps per scheduler hide each other's TMEM-load / max / store phases, so the MUFU
+// pipe idles less.
+template <int SPLIT>
+struct A2Cfg {
+  static constexpr int SM_WARPS = 8 * SPLIT;        // softmax warps
+  static constexpr int TMA_WARP = SM_WARPS;
+  static constexpr int MMA_WARP0 = SM_WARPS + 1;    // + tile index
+  static constexpr int THREADS = (SM_WARPS + 3) * 32;
+  static constexpr int COLS = A2_BK / SPLIT;        // S columns per softmax thread
+};
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 lanes x K) is read from tensor memory, two fp16 per column
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -55,7 +67,8 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(A2_THREADS, 1)
+template <int SPLIT>
+__global__ void __launch_bounds__(A2Cfg<SPLIT>::THREADS, 1)
 attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,6 +87,8 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* pv_done = p_ready + 2;           // [2]  O_t += P_t(j) V_j retired
   uint64_t* s_free = pv_done + 2;            // [2]  S_t(j) is in registers (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  float* xch = reinterpret_cast<float*>(tmem_slot + 2);  // [2 parity][2 tiles][2 halves][128 rows] (SPLIT == 2)
+  using Cfg = A2Cfg<SPLIT>;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,7 +97,7 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int img = blockIdx.z;
   const int row_base = img * p.S;  // first token row of this image in the qkv matrix
 
-  if (warp == 8 && lane == 0) {
+  if (warp == Cfg::TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
@@ -94,13 +109,13 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_ready[t], 128);
+      mbar_init(&p_ready[t], 128 * SPLIT);
       mbar_init(&pv_done[t], 1);
-      mbar_init(&s_free[t], 128);
+      mbar_init(&s_free[t], 128 * SPLIT);
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == Cfg::MMA_WARP0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -109,7 +124,7 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * A2_Q_BYTES);
@@ -126,10 +141,10 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_2d(sV + s * A2_KV_BYTES, &tmKV, &v_full[s], p.v_off + head * 64, row_base + j * A2_BK);
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp >= Cfg::MMA_WARP0) {
     // ------------------------------------------------------------------ MMA issuers (one per query tile)
     if (lane == 0) {
-      const int t = warp - 9;
+      const int t = warp - Cfg::MMA_WARP0;
       constexpr uint32_t idesc_s = make_idesc_f16(A2_BK, false);  // S: N = 128 keys, K-major B
       constexpr uint32_t idesc_o = make_idesc_f16(64, true);      // O: N = 64 dims, V read MN-major
       const uint32_t q_addr = smem_u32(sQ + t * A2_Q_BYTES);
@@ -169,38 +184,45 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax (warps 0..7)
-    const int t = warp >> 2;                       // query tile
+    // ------------------------------------------------------------------ softmax
+    constexpr int COLS = Cfg::COLS;
+    const int t = warp / (4 * SPLIT);              // query tile
+    const int hf = SPLIT == 2 ? (warp >> 2) & 1 : 0;  // which half of the 128 key columns this thread owns
     const int r = (warp & 3) * 32 + lane;          // row in tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tmem_S = tmem_base + t * 128 + lane_sel;
-    const uint32_t tmem_O = tmem_base + 256 + t * 64 + lane_sel;
-    const uint32_t tmem_P = tmem_base + 384 + t * 64 + lane_sel;
+    const uint32_t tmem_S = tmem_base + t * 128 + hf * COLS + lane_sel;
+    const uint32_t tmem_O = tmem_base + 256 + t * 64 + hf * (64 / SPLIT) + lane_sel;
+    const uint32_t tmem_P = tmem_base + 384 + t * 64 + hf * (COLS / 2) + lane_sel;
+    const int pair_bar = 1 + t * 4 + (warp & 3);   // named barrier of the two warps sharing these rows
     float m_used = -CUDART_INF_F;
     float l_run = 0.f;
     for (int j = 0; j < p.n_kv; ++j) {
-      const int valid = p.S - j * A2_BK;  // keys [0, valid) of this block are real
+      const int valid = p.S - j * A2_BK - hf * COLS;  // my columns [0, valid) of this block are real keys
       mbar_wait(&s_full[t], j & 1, 49);
       tc_fence_after();
-      uint32_t v[128];
+      uint32_t v[COLS];
       {
         uint32_t(*v4)[32] = reinterpret_cast<uint32_t(*)[32]>(v);
-        tmem_ld_x32(tmem_S, v4[0]);
-        tmem_ld_x32(tmem_S + 32, v4[1]);
-        tmem_ld_x32(tmem_S + 64, v4[2]);
-        tmem_ld_x32(tmem_S + 96, v4[3]);
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) tmem_ld_x32(tmem_S + c * 32, v4[c]);
         tmem_ld_wait();
       }
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // the tensor core may overwrite S_t with block j+1 now
-      if (valid < A2_BK) {  // warp-uniform: only the last key block of an image can be partial
+      if (valid < COLS) {  // warp-uniform: only the last key block of an image can be partial
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < COLS; ++i)
           if (i >= valid) v[i] = 0xff800000u;  // -inf
       }
       float mx = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmax3(mx, __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      for (int i = 0; i < COLS / 2; ++i) mx = fmax3(mx, __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      if constexpr (SPLIT == 2) {
+        float* slot = xch + ((j & 1) * 2 + t) * 256;  // parity double buffer: a slot is rewritten two blocks later
+        slot[hf * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, slot[(hf ^ 1) * 128 + r]);
+      }
       const float m_blk = mx * p.scale_log2;
       bool raise = false;
       if (j == 0)
@@ -216,7 +238,7 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         m_used = m_new;
         l_run *= alpha;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {  // 16 columns at a time: this rare path must not cost the main loop registers
+        for (int c = 0; c < 4 / SPLIT; ++c) {  // 16 columns at a time: this rare path must not cost the main loop registers
           uint32_t o[16];
           tmem_ld_x16(tmem_O + c * 16, o);
           tmem_ld_wait();
@@ -229,9 +251,9 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // probabilities -> packed fp16 -> this tile's P columns
       const float neg_m = -m_used;
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[COLS / 2];
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
+      for (int i = 0; i < COLS / 2; i += 2) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
         const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
         const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, neg_m));
@@ -250,8 +272,8 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       {
         const uint32_t(*pk2)[32] = reinterpret_cast<const uint32_t(*)[32]>(pk);
-        tmem_st_x32(tmem_P, pk2[0]);
-        tmem_st_x32(tmem_P + 32, pk2[1]);
+#pragma unroll
+        for (int c = 0; c < COLS / 64; ++c) tmem_st_x32(tmem_P + c * 32, pk2[c]);
         tmem_st_wait();
       }
       tc_fence_before();
@@ -259,11 +281,17 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     mbar_wait(&pv_done[t], (p.n_kv - 1) & 1, 51);
     tc_fence_after();
+    if constexpr (SPLIT == 2) {  // row sum = the two halves' sums (same reference maximum on both sides)
+      float* slot = xch + (((p.n_kv & 1) * 2) + t) * 256;
+      slot[hf * 128 + r] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l_run += slot[(hf ^ 1) * 128 + r];
+    }
     const float inv_l = 1.0f / l_run;
     const int q = q0 + t * A2_BQ + r;
-    __half* dst = p.out + static_cast<long long>(row_base + q) * p.ldo + head * 64;
+    __half* dst = p.out + static_cast<long long>(row_base + q) * p.ldo + head * 64 + hf * (64 / SPLIT);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 2 / SPLIT; ++c) {  // each thread writes its 64 / SPLIT output dims
       uint32_t o[32];
       tmem_ld_x32(tmem_O + c * 32, o);
       tmem_ld_wait();
@@ -282,13 +310,25 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == Cfg::MMA_WARP0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-int launch_attn_spatial2(const svdpp_attn_desc* d, cudaStream_t stream) {
+template <int SPLIT>
+static int launch_a2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Attn2Params& p, dim3 grid, cudaStream_t stream) {
+  auto kern = attn_spatial2_tc_kernel<SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, A2Cfg<SPLIT>::THREADS, A2_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  return check_launch("attn_spatial2_tc_kernel");
+}
+
+int launch_attn_spatial2(const svdpp_attn_desc* d, int split, cudaStream_t stream) {
   SVDPP_CHECK_ARG(d->heads <= 65535 && d->n_img <= 65535, "attn: grid too large");
   Attn2Params p{};
   p.S = d->S;
@@ -307,14 +347,9 @@ int launch_attn_spatial2(const svdpp_attn_desc* d, cudaStream_t stream) {
   uint32_t box_kv[2] = {64, A2_BK};
   if (encode_tmap_f16(&tmQ, d->qkv, 2, dims, str, box_q)) return -5;
   if (encode_tmap_f16(&tmKV, d->qkv, 2, dims, str, box_kv)) return -5;
-  static bool configured = false;
-  if (!configured) {
-    SVDPP_CUDA(cudaFuncSetAttribute(attn_spatial2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
-    configured = true;
-  }
   dim3 grid((d->S + 2 * A2_BQ - 1) / (2 * A2_BQ), d->heads, d->n_img);
-  attn_spatial2_tc_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
-  return check_launch("attn_spatial2_tc_kernel");
+  if (split == 2) return launch_a2<2>(tmQ, tmKV, p, grid, stream);
+  return launch_a2<1>(tmQ, tmKV, p, grid, stream);
 }
 
 }  // namespace svdpp
