@@ -62,11 +62,32 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Measured dead end: evaluating every fourth (or eighth) exponential with a degree-3 polynomial on the FMA pipe
+// (poly3_exp2) to relieve the MUFU pipe was SLOWER (774 vs 799 TFLOP/s): the softmax warps run out of issue
+// slots before the MUFU pipe (73 % busy) saturates.
 template <int SPLIT>
 __global__ void __launch_bounds__(A2Cfg<SPLIT>::THREADS, 1)
 attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
@@ -250,22 +271,48 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       // probabilities -> packed fp16 -> this tile's P columns
       const float neg_m = -m_used;
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
       uint32_t pk[COLS / 2];
+      if constexpr (SPLIT == 1) {
+        // packed f32x2 arithmetic (FFMA2 / FADD2) halves the issue slots of the scale-and-shift and of the row
+        // sum: 752 -> 807 TFLOP/s at S = 9216.  (With two threads per row the 64-bit register pairs push the
+        // 96-register budget into spills: 799 -> 717, so that variant keeps scalar arithmetic.)
+        const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
+        const uint64_t negm2 = pack_f2(neg_m, neg_m);
+        uint64_t lsa = 0ull, lsb = 0ull;  // (0.f, 0.f)
 #pragma unroll
-      for (int i = 0; i < COLS / 2; i += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
-        const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, neg_m));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), p.scale_log2, neg_m));
-        ls0 += p0;
-        ls1 += p1;
-        ls2 += p2;
-        ls3 += p3;
-        pk[i] = pack_half2(p0, p1);
-        pk[i + 1] = pack_half2(p2, p3);
+        for (int i = 0; i < COLS / 2; i += 2) {
+          const uint64_t xa = ffma2(pack_f2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2);
+          const uint64_t xb = ffma2(pack_f2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), scale2, negm2);
+          float x0, x1, x2, x3;
+          unpack_f2(xa, x0, x1);
+          unpack_f2(xb, x2, x3);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+          lsa = fadd2(lsa, pack_f2(p0, p1));
+          lsb = fadd2(lsb, pack_f2(p2, p3));
+          pk[i] = pack_half2(p0, p1);
+          pk[i + 1] = pack_half2(p2, p3);
+        }
+        float a0, a1, b0, b1;
+        unpack_f2(lsa, a0, a1);
+        unpack_f2(lsb, b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
+      } else {
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < COLS / 2; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, neg_m));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), p.scale_log2, neg_m));
+          ls0 += p0;
+          ls1 += p1;
+          ls2 += p2;
+          ls3 += p3;
+          pk[i] = pack_half2(p0, p1);
+          pk[i + 1] = pack_half2(p2, p3);
+        }
+        l_run += (ls0 + ls1) + (ls2 + ls3);
       }
-      l_run += (ls0 + ls1) + (ls2 + ls3);
       if (j > 0) {  // P_t(j-1) must have been consumed (long since: it was issued a whole exp phase ago)
         mbar_wait(&pv_done[t], (j - 1) & 1, 52);
         tc_fence_after();

@@ -11,6 +11,7 @@
 // Convolutions never materialise im2col: for tap (dw,dh,df) the producer loads the activation
 // window shifted by the tap through a 5-D tensor map [C, W, H, F, B]; TMA zero-fills the halo.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -37,21 +38,25 @@ struct GemmParams {
   long long ldd;
   int n_store;
   int m_tiles, n_tiles;
+  int prefetch_r1;  // producer warp pulls the residual tile into L2 one main loop ahead of the epilogue
 };
 
-// Exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational form of erfc (|error| < 1.5e-7,
-// far below the fp16 rounding that follows): 2 MUFU + ~12 FMA-pipe instructions and no branches, about a
-// third of erff()'s cost, which otherwise makes the GEGLU epilogue slower than its K=320 main loop.
+// Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
+// a = |x|, with Phi(-a) = 2^Q(a), Q a degree-6 minimax fit of log2 Phi(-a) on [0, 5.5] (relative error of Phi
+// 2.6e-5, 20x below the fp16 rounding that follows; max abs error 3.8e-6 over every fp16 input; fitted and
+// checked by tools/fit_gelu.py).  For a > 5.5 the term is below 1e-7 and a is clamped.  The Abramowitz-Stegun
+// erfc form used before cost 16 instructions and two MUFU, which made the GEGLU epilogue of the K = 320 layers
+// (128 x 128 outputs, 2 x 16384 MUFU per tile = 2048 cycles against a 2560-cycle main loop) the bound of the
+// largest GEMMs of the network.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float half_erfc = 0.5f * poly * t * fast_exp2(z * z * -1.4426950408889634f);  // 0.5*erfc(|x|/sqrt2)
-  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return x * phi;
+  const float a = fminf(fabsf(x), 5.5f);
+  float q = fmaf(a, 2.6153752e-05f, -6.6098123e-04f);
+  q = fmaf(q, a, 7.4883099e-03f);
+  q = fmaf(q, a, -5.1970404e-02f);
+  q = fmaf(q, a, -4.6032947e-01f);
+  q = fmaf(q, a, -1.1505840e+00f);
+  q = fmaf(q, a, -1.0000361e+00f);
+  return fmaf(-a, fast_exp2(q), fmaxf(x, 0.f));
 }
 
 // torch fp16 semantics of GEGLU: proj output rounded to fp16, gelu(gate) rounded, product rounded
@@ -85,7 +90,7 @@ __device__ __forceinline__ void load8(const __half* p, float (&o)[8]) {
 // and HALF of the B tile, the leader issues M = 256 MMAs that read B from both CTAs' smem, and each CTA
 // keeps the accumulator of its own 128 rows in its own TMEM.  Per SM and k-block this moves 26 KB instead of
 // 36 KB from L2 (the L2 -> SM path, not the tensor pipe, caps the one-CTA kernel near 1 PFLOP/s).
-template <int BN, bool GEGLU, bool TWO>
+template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -102,13 +107,19 @@ struct GemmCfg {
   static constexpr int C_PITCH = SW + 8;
   static constexpr int C_BYTES = BM * C_PITCH * 2;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 1024 /*barriers + bias tile*/;
+  // Epilogue warps: the GEGLU epilogue (two accumulators, exact GELU, fp16 roundings per output) needs about as
+  // many issue slots per tile as the K = 320 main loop has cycles; with 8 warps (2 per scheduler) dependency
+  // stalls made it the bound.  It uses few registers, so the 256-wide variant runs 16 epilogue warps.
+  static constexpr int EPI_WARPS = EW_ ? EW_ : ((GEGLU && BN == 256) ? 16 : 8);
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 128 + EPI_THREADS;
 };
 
-template <int BN, bool GEGLU, bool TWO>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
+__global__ void __launch_bounds__(GemmCfg<BN, GEGLU, TWO, EW_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, GEGLU, TWO>;
+  using Cfg = GemmCfg<BN, GEGLU, TWO, EW_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __half* sC = reinterpret_cast<__half*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -140,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], TWO ? 512 : 256);  // pairs: both CTAs' epilogue threads, on the leader
+      mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS);  // pairs: both CTAs' epilogue threads, on the leader
     }
     fence_mbar_init();
   }
@@ -181,6 +192,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = row / p.cH;
         cf = img % p.cF;
         cb = img / p.cF;
+      }
+      if (!GEGLU && p.prefetch_r1) {
+        // the epilogue of this tile will read R1[m0 .. m0+127][n0 .. n0+BN) a whole main loop from now: start the
+        // HBM -> L2 fetch here so that its loads find the lines in L2 (K = 320 layers are epilogue-latency bound)
+        const int n_first = (w % p.n_tiles) * BN;
+        constexpr int LPR = (BN * 2 + 127) / 128;  // 128-byte lines per tile row
+        for (int i = lane; i < Cfg::BM * LPR; i += 32) {
+          const int r = i / LPR, l = i - r * LPR;
+          if (m0 + r < p.M && n_first + l * 64 < p.n_store)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + static_cast<long long>(m0 + r) * p.ldr1 + n_first + l * 64));
+        }
       }
       int tap = 0, kc = 0;  // k-block = (tap, kc)
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -282,16 +304,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // buffer (the TMEM stage is released after the last round), (3) coalesced copy of the staging buffer
     // to global.  Thread = accumulator row; the two warps of a lane quarter take alternate column chunks.
     const int we = warp & 3;          // the TMEM lane quarter this warp may read (warp % 4)
-    const int half = (warp - 4) >> 2;  // 0: even column chunks, 1: odd column chunks
+    constexpr int EW = Cfg::EPI_WARPS, ET = Cfg::EPI_THREADS, WPQ = EW / 4;  // WPQ warps share a TMEM lane quarter
+    const int half = (warp - 4) >> 2;  // which of the quarter's WPQ warps: takes column chunks half, half + WPQ, ...
     const int row = we * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..255
+    const int et = threadIdx.x - 128;  // 0..ET-1
     constexpr int SW = Cfg::SW;
     constexpr int VPR = SW / 8;         // 16-byte vectors per staged row
     constexpr int CW = GEGLU ? 8 : 16;  // columns per chunk
-    constexpr int NCH = SW / CW / 2;    // chunks per warp and round
-    constexpr int NV = Cfg::BM * VPR / 256;  // staged vectors per thread
-    static_assert(Cfg::BM * VPR % 256 == 0 && (SW / CW) % 2 == 0, "epilogue work split");
-    auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    constexpr int NCH = SW / CW / WPQ;  // chunks per warp and round
+    constexpr int NV = Cfg::BM * VPR / ET;  // staged vectors per thread
+    static_assert(Cfg::BM * VPR % ET == 0 && (SW / CW) % WPQ == 0, "epilogue work split");
+    auto epi_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); };
     int as = 0;
     uint32_t aphase = 0;
     for (int w = work_first; w < work_total; w += work_stride) {
@@ -327,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (rv_row != nullptr) {
 #pragma unroll
             for (int ci = 0; ci < NCH; ++ci) {
-              const int c = half + 2 * ci;
+              const int c = half + WPQ * ci;
 #pragma unroll
               for (int hlf = 0; hlf < CW / 8; ++hlf)
                 rvv[ci][hlf] = (nout0 + c * CW < p.n_store)
@@ -340,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint4 val[NV];  // all loads in flight at once
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-              const int i = et + k * 256;
+              const int i = et + k * ET;
               const int r = i / VPR, v = i - r * VPR;
               val[k] = make_uint4(0, 0, 0, 0);
               if (m_base + r < p.M) {
@@ -356,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-              const int i = et + k * 256;
+              const int i = et + k * ET;
               const int r = i / VPR, v = i - r * VPR;
               *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
             }
@@ -369,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
-          const int c = half + 2 * ci;
+          const int c = half + WPQ * ci;
           uint32_t v[CW];
           uint32_t g[CW];
           if constexpr (GEGLU) {
@@ -455,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(&tempty[as]);  // accumulator stage free: the next tile's MMAs may start
         }
         epi_bar();
-        for (int i = et; i < Cfg::BM * VPR; i += 256) {
+        for (int i = et; i < Cfg::BM * VPR; i += ET) {
           const int r = i / VPR, v = i - r * VPR;
           if (m_base + r < p.M) {
             const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
@@ -570,12 +593,12 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   e.D[static_cast<long long>(m) * e.ldd + nout] = o;
 }
 
-template <int BN, bool GEGLU, bool TWO>
+template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, GEGLU, TWO>;
+  using Cfg = GemmCfg<BN, GEGLU, TWO, EW_>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, GEGLU, TWO>;
+  auto kern = gemm_tc_kernel<BN, GEGLU, TWO, EW_>;
   if (!configured) {
     SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -586,7 +609,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     if (pairs < clusters) clusters = pairs;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -601,7 +624,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -615,7 +638,8 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   // impl 3: CTA pairs with 256-wide tiles (N must be a multiple of 256; GEGLU weights interleaved per 128)
   // impl 4: one CTA per 128x128 tile (N a multiple of 128; no GEGLU) - for small M, where 128x128 tiles fill the
   //         148 SMs' last wave better than 128x160 or 256x256
-  const int BN = impl == 3 ? 256 : (impl == 4 ? 128 : 160);
+  // impl 5: impl 3 with 8 instead of 16 GEGLU epilogue warps (A/B measurements only)
+  const int BN = (impl == 3 || impl == 5) ? 256 : (impl == 4 ? 128 : 160);
   SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
   SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
   SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
@@ -648,6 +672,10 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   p.n_store = n_store;
   p.m_tiles = (d->M + 127) / 128;
   p.n_tiles = d->N / BN;
+  {
+    static const bool no_prefetch = getenv("SVDPP_NO_R1_PREFETCH") != nullptr;
+    p.prefetch_r1 = (p.R1 != nullptr && !no_prefetch && d->K <= 640) ? 1 : 0;  // measured: K=320 +20 %, 640 +6 %, 1280 -3 %
+  }
 
   if (d->conv) {
     SVDPP_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= SVDPP_MAX_TAPS, "gemm: ntaps=%d", d->ntaps);
@@ -661,7 +689,7 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     p.cW = d->cW;
   }
 
-  if (impl == 3) {
+  if (impl == 3 || impl == 5) {
     SVDPP_CHECK_ARG(d->N % 256 == 0, "gemm: impl 3 needs N %% 256 == 0 (N=%d)", d->N);
   }
   if (impl == 1) {
@@ -694,9 +722,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
     return check_launch("gemm_simt_kernel");
   }
-  SVDPP_CHECK_ARG(impl == 0 || impl == 2 || impl == 3 || impl == 4, "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(impl == 0 || (impl >= 2 && impl <= 5), "gemm: unknown impl %d", impl);
   SVDPP_CHECK_ARG(!(impl == 4 && d->geglu), "gemm: impl 4 has no GEGLU epilogue");
-  const bool two = impl == 2 || impl == 3;  // CTA pairs (cta_group::2)
+  const bool two = impl == 2 || impl == 3 || impl == 5;  // CTA pairs (cta_group::2)
 
   CUtensorMap tmA, tmA2, tmB;
   if (!d->conv) {
@@ -743,7 +771,11 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
   }
   if (impl == 4) return launch_tc<128, false, false>(tmA, tmA2, tmB, p, stream);
+  if (impl == 5 && d->geglu) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
+  if (impl == 5) return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 3) {
+    // 16 epilogue warps pay off only where the epilogue outweighs the main loop (K = 320: +5 %; K >= 640: -1.5 %)
+    if (d->geglu && d->K > 384) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
     if (d->geglu) return launch_tc<256, true, true>(tmA, tmA2, tmB, p, stream);
     return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
   }
