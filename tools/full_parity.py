@@ -28,7 +28,7 @@ def diff(a, b):
                 cos=Fn.cosine_similarity(a.flatten(), b.flatten(), dim=0).item(), ref_absmax=b.abs().max().item())
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=14)
     ap.add_argument("--height", type=int, default=72)
@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--guidance-scale", type=float, default=None)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--out", default="full_parity.json")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     dev = torch.device("cuda", 0)
     F_, H, W, T = a.frames, a.height, a.width, a.steps
     torch.manual_seed(0)
@@ -94,6 +94,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", a.out), "w"), indent=1)
     print(json.dumps({k: v for k, v in res.items() if k != "per_step"}, indent=1))
+    return res
 
 
 if __name__ == "__main__":

@@ -4,12 +4,23 @@
 // fp32 statistics, deterministic (no floating-point atomics).
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.h"
 
 namespace svdpp {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// SiLU with ONE MUFU op: x*sigmoid(x) = h*tanh(h) + h, h = x/2 (tanh.approx.f32, relative error 2^-11, below the
+// fp16 rounding of the result).  The exp + reciprocal form costs two MUFU per element, and at 16 MUFU/clk/SM that
+// - not HBM - bound the GroupNorm+SiLU apply pass (ncu: 63.6 us for 295 MB at level 0).
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -49,126 +60,207 @@ __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const 
   return c0 < C1 ? x1 + pix * C1 + c0 : x2 + pix * C2 + (c0 - C1);
 }
 
-// partial[n][chunk][g] = (sum, sumsq) over the chunk's pixels and the group's channels.  The last block to finish
-// an image reduces that image's chunks (fixed order, fp64); for the temporal GroupNorm (statistics over
-// frames_per_stat images) the last image to finish reduces the per-image sums.  -> stats[st][g] = (mean, rstd).
-// No separate finalize launch; every counter is left at zero for the next call.
+// Statistics pass.  Work item = (image n, chunk of `pix` pixels), items numbered image-major.  Persistent blocks
+// (two per SM); block c owns the contiguous item range [c*ipc, (c+1)*ipc) and streams it through a two-slot
+// shared-memory ring: a chunk is one contiguous range of each source, so thread 0 fetches the NEXT item with (at
+// most two) bulk async copies on an mbarrier while the block adds up the current one.  Per-thread channel sums stay
+// in registers across all chunks of an image; only when the image changes (once or twice per block) are they
+// reduced to partial[n][slot][g] = (sum, sumsq), slot = block - first block of image n.  The last block to finish
+// an image reduces that image's slots (fixed order, fp64); for the temporal GroupNorm (statistics over
+// frames_per_stat images) the last image to finish reduces the per-image sums -> stats[st][g] = (mean, rstd).
+// No finalize launch, no floating-point atomics (deterministic); counters are left at zero for the next call.
+// History (ncu, level 0, 147 MB read): register-staged loads, one chunk per block, per-chunk reduce + fence +
+// atomic: 55.9 us; one bulk copy per block: 50.1 us (a wave's blocks all fetch, then all compute).
+__device__ __forceinline__ void gn_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(512)
 gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int pix,
-                  float2* partial, double2* imgsum, unsigned* counters, int frames_per_stat, float count, float eps,
-                  float2* __restrict__ stats) {
-  extern __shared__ float2 red[];  // [rows][C]
+                  int n_chunks, int n_items, int ipc, int n_slots, float2* partial, double2* imgsum, unsigned* counters,
+                  int frames_per_stat, float count, float eps, float2* __restrict__ stats) {
+  extern __shared__ __align__(128) uint8_t gn_smem[];
   __shared__ int s_last;
+  __shared__ __align__(8) uint64_t s_bar[8];
+  const int begin = blockIdx.x * ipc;
+  const int end = min(begin + ipc, n_items);
+  if (begin >= end) return;
   const int C = C1 + C2;
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
-  const int n = blockIdx.y;
-  const int p0 = blockIdx.x * pix;
-  const int p1 = min(p0 + pix, HW);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int max_slots = n_chunks + 1;
+  const uint32_t slot_bytes = static_cast<uint32_t>(pix) * C * 2;
+  float2* red = reinterpret_cast<float2*>(gn_smem + n_slots * slot_bytes);  // [rows][C]; later the fp64 finalize scratch
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(gn_smem));
+  const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
+
+  auto issue = [&](int item, int slot) {  // thread 0 only
+    const int n = item / n_chunks, ch = item - n * n_chunks;
+    const int p0 = ch * pix;
+    const int npx = min(pix, HW - p0);
+    const uint32_t b1 = static_cast<uint32_t>(npx) * C1 * 2, b2 = static_cast<uint32_t>(npx) * C2 * 2;
+    const uint32_t bar = bar0 + slot * 8, dst = smem0 + slot * slot_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b1 + b2) : "memory");
+    gn_bulk_load(dst, x1 + (static_cast<long long>(n) * HW + p0) * C1, b1, bar);
+    if (C2 > 0) gn_bulk_load(dst + pix * C1 * 2, x2 + (static_cast<long long>(n) * HW + p0) * C2, b2, bar);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < n_slots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + i * 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < n_slots - 1 && begin + i < end; ++i) issue(begin + i, i);  // ring prologue
+  }
+  __syncthreads();  // barriers initialised before anyone polls them
+
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  for (int pb = p0 + threadIdx.y; pb < p1; pb += 4 * rows) {
-    uint4 u[4];
+
+  // block-level reduction of the register sums of image n, partial write, arrival count, finalize by the last block
+  auto flush = [&](int n) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {  // four independent 16-byte loads in flight
-      const int p = pb + t * rows;
-      u[t] = p < p1 ? *reinterpret_cast<const uint4*>(gn_src(x1, C1, x2, C2, static_cast<long long>(n) * HW + p, c0))
-                    : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 8; ++j) red[threadIdx.y * C + c0 + j] = make_float2(s[j], ss[j]);
+    __syncthreads();
+    const int first_blk = (n * n_chunks) / ipc;
+    const int n_blk = ((n + 1) * n_chunks - 1) / ipc - first_blk + 1;  // blocks that hold a piece of image n
+    {
+      // group sums: LPG lanes per group walk the group's rows x channels entries in a fixed interleave and
+      // combine with shuffles
+      const int lpg = nthreads >= 128 ? 4 : (nthreads >= 64 ? 2 : 1);
+      if (tid < GN_GROUPS * lpg) {
+        const int g = tid / lpg, j = tid - g * lpg;
+        const int cpg = C / GN_GROUPS;
+        const int items = rows * cpg;
+        float a = 0.f, b = 0.f;
+        for (int it = j; it < items; it += lpg) {
+          const int r = it / cpg, i = it - r * cpg;
+          const float2 v = red[r * C + g * cpg + i];
+          a += v.x;
+          b += v.y;
+        }
+        for (int o = 1; o < lpg; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (j == 0) {
+          const int slot = static_cast<int>(blockIdx.x) - first_blk;
+          partial[(static_cast<long long>(n) * max_slots + slot) * GN_GROUPS + g] = make_float2(a, b);
+          __threadfence();
+        }
+      }
     }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned old = atomicAdd(&counters[n], 1u);
+      s_last = old == static_cast<unsigned>(n_blk - 1);
+      if (s_last) counters[n] = 0u;
+    }
+    __syncthreads();
+    if (s_last) {  // block-uniform: this block completed image n
+      __threadfence();
+      double a = 0.0, b = 0.0;
+      if (tid < GN_GROUPS) {
+        const float2* base = partial + static_cast<long long>(n) * max_slots * GN_GROUPS + tid;
+        for (int i = 0; i < n_blk; ++i) {
+          const float2 v = __ldcg(base + static_cast<long long>(i) * GN_GROUPS);
+          a += v.x;
+          b += v.y;
+        }
+      }
+      const int st = n / frames_per_stat;
+      bool emit = true;
+      if (frames_per_stat > 1) {
+        if (tid < GN_GROUPS) {
+          imgsum[n * GN_GROUPS + tid] = make_double2(a, b);
+          __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned old = atomicAdd(&counters[GN_MAX_STATS + st], 1u);
+          s_last = old == static_cast<unsigned>(frames_per_stat - 1);
+          if (s_last) counters[GN_MAX_STATS + st] = 0u;
+        }
+        __syncthreads();
+        emit = s_last != 0;
+        if (emit) {
+          __threadfence();
+          if (tid < GN_GROUPS) {
+            a = 0.0;
+            b = 0.0;
+            for (int f = 0; f < frames_per_stat; ++f) {
+              const double2 v = __ldcg(imgsum + (static_cast<long long>(st) * frames_per_stat + f) * GN_GROUPS + tid);
+              a += v.x;
+              b += v.y;
+            }
+          }
+        }
+      }
+      if (emit && tid < GN_GROUPS) {
+        const double mean = a / count;
+        double var = b / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[st * GN_GROUPS + tid] = make_float2(static_cast<float>(mean),
+                                                  static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+      }
+    }
+    __syncthreads();  // scratch and s_last are free again
+  };
+
+  int slot = 0;
+  uint32_t phases = 0u;  // bit i = parity to wait for on slot i
+  int cur = begin / n_chunks;
+  for (int item = begin; item < end; ++item) {
+    const int n = item / n_chunks, ch = item - n * n_chunks;
+    if (n != cur) {
+      flush(cur);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+      for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+      cur = n;
+    }
+    const int npx = min(pix, HW - ch * pix);
+    // keep n_slots - 1 items in flight; the slot refilled here was consumed before the barrier that ended the
+    // previous iteration
+    if (tid == 0 && item + n_slots - 1 < end) {
+      int ns = slot + n_slots - 1;
+      if (ns >= n_slots) ns -= n_slots;
+      issue(item + n_slots - 1, ns);
+    }
+    {
+      const uint32_t bar = bar0 + slot * 8;
+      const uint32_t ph = (phases >> slot) & 1u;
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(ph)
+            : "memory");
+      phases ^= 1u << slot;
+    }
+    const __half* s1 = reinterpret_cast<const __half*>(gn_smem + slot * slot_bytes);  // [npx][C1]
+    const __half* s2 = s1 + static_cast<size_t>(pix) * C1;                             // [npx][C2]
+    const __half* src = c0 < C1 ? s1 + c0 : s2 + (c0 - C1);
+    const int pitch = c0 < C1 ? C1 : C2;
+#pragma unroll 4
+    for (int p = threadIdx.y; p < npx; p += rows) {
       float v[8];
-      unpack8(u[t], v);
+      unpack8(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * pitch), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j] += v[j];
         ss[j] += v[j] * v[j];
       }
     }
+    __syncthreads();  // slot consumed
+    if (++slot == n_slots) slot = 0;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.y * C + c0 + j] = make_float2(s[j], ss[j]);
-  __syncthreads();
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int n_chunks = gridDim.x;
-  if (tid < GN_GROUPS) {
-    const int cpg = C / GN_GROUPS;
-    float a = 0.f, b = 0.f;
-    for (int r = 0; r < rows; ++r)
-      for (int i = 0; i < cpg; ++i) {
-        const float2 v = red[r * C + tid * cpg + i];
-        a += v.x;
-        b += v.y;
-      }
-    partial[(static_cast<long long>(n) * n_chunks + blockIdx.x) * GN_GROUPS + tid] = make_float2(a, b);
-    __threadfence();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned old = atomicAdd(&counters[n], 1u);
-    s_last = old == static_cast<unsigned>(n_chunks - 1);
-    if (s_last) counters[n] = 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int nthreads = blockDim.x * blockDim.y;
-  const int parts = nthreads >> 5;  // >= 1: blocks have at least 32 threads
-  double* sa = reinterpret_cast<double*>(red);  // [parts][32] sums, then [parts][32] sums of squares
-  double* sb = sa + parts * GN_GROUPS;
-  const int g = tid & 31, part = tid >> 5;
-  if (part < parts) {
-    const float2* base = partial + static_cast<long long>(n) * n_chunks * GN_GROUPS + g;
-    double a = 0.0, b = 0.0;
-    for (int i = part; i < n_chunks; i += parts) {
-      const float2 v = __ldcg(base + static_cast<long long>(i) * GN_GROUPS);
-      a += v.x;
-      b += v.y;
-    }
-    sa[part * GN_GROUPS + g] = a;
-    sb[part * GN_GROUPS + g] = b;
-  }
-  __syncthreads();
-  double a = 0.0, b = 0.0;
-  if (tid < GN_GROUPS) {
-    for (int i = 0; i < parts; ++i) {
-      a += sa[i * GN_GROUPS + tid];
-      b += sb[i * GN_GROUPS + tid];
-    }
-  }
-  const int st = n / frames_per_stat;
-  if (frames_per_stat > 1) {
-    if (tid < GN_GROUPS) {
-      imgsum[n * GN_GROUPS + tid] = make_double2(a, b);
-      __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned old = atomicAdd(&counters[GN_MAX_STATS + st], 1u);
-      s_last = old == static_cast<unsigned>(frames_per_stat - 1);
-      if (s_last) counters[GN_MAX_STATS + st] = 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid < GN_GROUPS) {
-      a = 0.0;
-      b = 0.0;
-      for (int f = 0; f < frames_per_stat; ++f) {
-        const double2 v = __ldcg(imgsum + (static_cast<long long>(st) * frames_per_stat + f) * GN_GROUPS + tid);
-        a += v.x;
-        b += v.y;
-      }
-    }
-  }
-  if (tid < GN_GROUPS) {
-    const double mean = a / count;
-    double var = b / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[st * GN_GROUPS + tid] = make_float2(static_cast<float>(mean),
-                                              static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-  }
+  flush(cur);
 }
 
 __global__ void __launch_bounds__(512)
@@ -211,7 +303,7 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float y = fmaf(v[j], sc[j], sh[j]);
-          v[j] = silu ? silu_f(y) : y;
+          v[j] = silu ? silu_fast(y) : y;
         }
         *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * HW + p) * C + c0) = pack8(v);
       }
@@ -650,8 +742,13 @@ static inline unsigned grid_for(long long n, int threads, int max_blocks = 148 *
 
 using namespace svdpp;
 
-static int gn_pixels_per_block(int n_img, int HW) {
-  int pix = GN_MAX_PIX;
+static int gn_pixels_per_block(int n_img, int HW, int C) {
+  static const int stats_max = [] {
+    const char* e = getenv("SVDPP_GN_STATS_PIX");
+    return e ? atoi(e) : GN_MAX_PIX;
+  }();
+  int pix = stats_max;
+  while (pix > GN_MIN_PIX && static_cast<long long>(pix) * C * 2 > 40 * 1024) pix >>= 1;  // ~40 KB of pixels per block
   while (pix > GN_MIN_PIX && static_cast<long long>(n_img) * ((HW + pix - 1) / pix) < 4LL * num_sms()) pix >>= 1;
   return pix;
 }
@@ -659,7 +756,7 @@ static int gn_pixels_per_block(int n_img, int HW) {
 extern "C" size_t svdpp_groupnorm_workspace_bytes(int32_t n_img, int32_t HW) {
   const size_t n_chunks = (static_cast<size_t>(HW) + GN_MIN_PIX - 1) / GN_MIN_PIX;  // worst case (smallest blocks)
   return GN_COUNTER_BYTES + static_cast<size_t>(n_img) * GN_GROUPS * sizeof(double2) +
-         (static_cast<size_t>(n_img) * n_chunks * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
+         (static_cast<size_t>(n_img) * (n_chunks + 1) * GN_GROUPS + static_cast<size_t>(n_img) * GN_GROUPS) * sizeof(float2);
 }
 
 extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
@@ -675,12 +772,12 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   SVDPP_CHECK_ARG(frames_per_stat >= 1 && n_img % frames_per_stat == 0, "groupnorm: frames_per_stat=%d", frames_per_stat);
   SVDPP_CHECK_ARG(workspace_bytes >= svdpp_groupnorm_workspace_bytes(n_img, HW), "groupnorm: workspace too small");
   SVDPP_CHECK_ARG(n_img <= GN_MAX_STATS, "groupnorm: more than %d images", GN_MAX_STATS);
-  const int pix = gn_pixels_per_block(n_img, HW);
+  const int pix = gn_pixels_per_block(n_img, HW, C);
   const int n_chunks = (HW + pix - 1) / pix;
   unsigned* counters = static_cast<unsigned*>(workspace);
   double2* imgsum = reinterpret_cast<double2*>(static_cast<uint8_t*>(workspace) + GN_COUNTER_BYTES);
   float2* partial = reinterpret_cast<float2*>(imgsum + static_cast<size_t>(n_img) * GN_GROUPS);
-  float2* stats = partial + static_cast<size_t>(n_img) * n_chunks * GN_GROUPS;
+  float2* stats = partial + static_cast<size_t>(n_img) * (n_chunks + 1) * GN_GROUPS;
   const int nvc = C / 8;
   int rows = 256 / nvc;
   if (rows < 1) rows = 1;
@@ -688,21 +785,44 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   while (nvc * rows < 32) ++rows;  // the in-kernel reductions need at least one full warp
   dim3 block(nvc, rows);
   dim3 grid(n_chunks, n_img);
-  const size_t red_bytes = static_cast<size_t>(rows) * C * sizeof(float2);
+  const size_t red_bytes = static_cast<size_t>(rows) * C * sizeof(float2);   // reduction scratch / fp64 finalize
+  static const int slots_env = [] {
+    const char* e = getenv("SVDPP_GN_SLOTS");
+    return e ? atoi(e) : 0;
+  }();
+  // ring depth: as many pixel slots as fit in ~80 KB (two blocks per SM), at least 2, at most 8
+  int n_slots = slots_env ? slots_env : static_cast<int>((80 * 1024) / (static_cast<size_t>(pix) * C * 2));
+  if (n_slots < 2) n_slots = 2;
+  if (n_slots > 8) n_slots = 8;
+  const size_t smem_bytes = static_cast<size_t>(n_slots) * pix * C * 2 + red_bytes;
   static bool configured = false;
   if (!configured) {
-    SVDPP_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SVDPP_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  SVDPP_CHECK_ARG(red_bytes <= 64 * 1024, "groupnorm: reduction buffer too large");
+  SVDPP_CHECK_ARG(smem_bytes <= 112 * 1024, "groupnorm: shared-memory tile too large");
   const float count = static_cast<float>(frames_per_stat) * HW * (C / GN_GROUPS);
-  gn_partial_kernel<<<grid, block, red_bytes, stream>>>(static_cast<const __half*>(x1), C1,
-                                                        static_cast<const __half*>(x2), C2, HW, pix, partial, imgsum,
-                                                        counters, frames_per_stat, count, eps, stats);
+  const int n_items = n_chunks * n_img;
+  int stat_blocks = 2 * num_sms();  // persistent: two blocks per SM, each prefetching its next chunk
+  if (stat_blocks > n_items) stat_blocks = n_items;
+  const int ipc = (n_items + stat_blocks - 1) / stat_blocks;  // contiguous items per block
+  gn_partial_kernel<<<stat_blocks, block, smem_bytes, stream>>>(static_cast<const __half*>(x1), C1,
+                                                                static_cast<const __half*>(x2), C2, HW, pix, n_chunks,
+                                                                n_items, ipc, n_slots, partial, imgsum, counters,
+                                                                frames_per_stat, count, eps, stats);
   if (int e = check_launch("gn_partial_kernel")) return e;
-  gn_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
+  // the apply pass may use larger blocks than the statistics pass (its per-block prologue - gamma, beta, statistics -
+  // amortises better); SVDPP_GN_APPLY_PIX overrides for experiments
+  static const int apply_max = [] {
+    const char* e = getenv("SVDPP_GN_APPLY_PIX");
+    return e ? atoi(e) : 64;
+  }();
+  int apix = pix;
+  while (apix < apply_max && static_cast<long long>(n_img) * ((HW + 2 * apix - 1) / (2 * apix)) >= 4LL * num_sms()) apix <<= 1;
+  dim3 grid_apply((HW + apix - 1) / apix, n_img);
+  gn_apply_kernel<<<grid_apply, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                              stats, static_cast<__half*>(out), HW, pix, frames_per_stat, apply_silu);
+                                              stats, static_cast<__half*>(out), HW, apix, frames_per_stat, apply_silu);
   return check_launch("gn_apply_kernel");
 }
 
