@@ -46,7 +46,9 @@ def parse_args():
     p.add_argument("--denoise-steps", type=int, default=25)
     p.add_argument("--guidance-scale", type=float, default=None)
     p.add_argument("--seed", type=int, default=42)
-    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--no-graph", action="store_true",
+                   help="enqueue every launch eagerly instead of replaying one CUDA graph per denoising step (within "
+                        "+-1 %%: the host runs ~740 launches per step ahead of the GPU either way)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-frames", type=int, default=2)
     p.add_argument("--schedule", default="ring", choices=["ring", "linear"],
@@ -414,9 +416,12 @@ def main() -> None:
         att = agg.get("attn_spatial")
         if att:
             result["roofline_attention"] = {
-                "kernel": "attn_spatial_tc_kernel (tcgen05 FMHA)", "bound": "tensor",
+                "kernel": "attn_spatial2_tc_kernel / attn_spatial_tc_kernel (tcgen05 FMHA)", "bound": "tensor",
                 "achieved": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12 / peak, "launches": att[2], "ms": att[0]}
+                "frac": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12 / peak, "launches": att[2], "ms": att[0],
+                # head_dim 64: one MUFU.EX2 per score (16/clk/SM, tools/ubench) against 256 tensor FLOP per score
+                "mufu_bound_tflops": 16 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * 256 / 1e12,
+                "note": "bound by the MUFU pipe before the tensor pipe; mufu_bound_tflops at the SM clock seen in the timed region"}
         result["kernel_ms_per_forward"] = {k: round(v[0], 3) for k, v in agg.items()}
         if F_ == 25 and (H, W) == (72, 128):
             try:   # achieved HBM GB/s of the bandwidth kernels at this workload's level-0 shapes (tools/bw_bench.py)
