@@ -34,7 +34,7 @@ def _cmp(got: torch.Tensor, ref: torch.Tensor, rel=2e-3, floor=1e-3):
 
 
 def _bn(impl):
-    return 256 if impl == 3 else (128 if impl == 4 else native.GEMM_BN)
+    return {3: 256, 5: 256, 4: 128, 6: 320}.get(impl, native.GEMM_BN)
 
 
 def _pad_n(w, mult=native.GEMM_BN):
@@ -373,6 +373,13 @@ ALL_CHECKS = {
     "bn128_gemm_split": lambda: gemm_linear(M=700, N=512, impl=4, K=384, split=True),
     "bn128_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=128, impl=4),
     "bn128_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=128, impl=4),
+    "pair320_gemm_plain": lambda: gemm_linear(M=512, N=320, K=64, impl=6, epilogue="bias"),
+    "pair320_gemm_linear": lambda: gemm_linear(M=300, N=320, K=320, impl=6),
+    "pair320_gemm_big": lambda: gemm_linear(M=4000, N=640, K=1280, impl=6),
+    "pair320_gemm_split": lambda: gemm_linear(M=700, N=320, impl=6, K=384, split=True),
+    "pair320_conv3x3_w32": lambda: conv3x3(Cout=320, impl=6),
+    "pair320_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=320, impl=6),
+    "pair320_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=320, impl=6),
     "tc_attn_spatial_256": lambda: attn_spatial(n_img=1, S=256, heads=1, impl=0),
     "tc_attn_spatial_tail": lambda: attn_spatial(n_img=2, S=320, heads=2, impl=0),
     "tc_attn_spatial_144": lambda: attn_spatial(n_img=3, S=144, heads=2, impl=0),

@@ -49,7 +49,7 @@ def linear_case(M, N, K, impls, residual=True):
     r = [torch.randn(M, N, device=DEV).half() for _ in range(n_sets)] if residual else None
     out = [torch.empty(M, N, device=DEV, dtype=torch.float16) for _ in range(n_sets)]
     for impl in impls:
-        bn = 256 if impl in (3, 5) else (128 if impl == 4 else 160)
+        bn = {3: 256, 5: 256, 4: 128, 6: 320}.get(impl, 160)
         if N % bn:
             continue
         ms = timed(lambda i: native.gemm(out[i], a[i], w, bias=b, r1=r[i] if residual else None, n_store=N, impl=impl), n_sets)
@@ -65,3 +65,7 @@ if __name__ == "__main__":
         for M, N, K in ((230400, 320, 320), (230400, 320, 1280), (230400, 960, 320), (57600, 640, 2560), (57600, 640, 640),
                         (14400, 1280, 5120), (3600, 1280, 1280)):
             linear_case(M, N, K, (0, 2, 3, 4))
+    if "wide" in what:   # the 256x320 pair tile against the one-CTA 128x160 tile on the N = 320 / 640 layers
+        for M, N, K in ((230400, 320, 2880), (230400, 320, 960), (230400, 320, 1280), (230400, 320, 640), (57600, 640, 5760),
+                        (57600, 640, 2560), (57600, 640, 1920), (57600, 640, 640), (230400, 960, 320), (14400, 1920, 1280)):
+            linear_case(M, N, K, (0, 6))

@@ -99,6 +99,15 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (TWO && BN <= 160) ? 6 : 5;
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
+  // BN = 320 (CTA pairs only): the whole N = 320 of the level-0 layers in one 256 x 320 pair tile, issued as two
+  // N = 160 MMAs per k-step.  Per CTA and k-block 36 KB come from L2 for 5.2 MFLOP (145 FLOP/B against 71 for the
+  // one-CTA 128x160 tile): the ~6300 B/clk L2->SM cap is what holds the narrow tiles near 0.9 PFLOP/s.  320 fp32
+  // columns leave room for ONE accumulator stage in the 512 TMEM columns, so TMEM reads of the epilogue are not
+  // overlapped with the next main loop (stores still are); worth it for K >= 1280.
+  static constexpr int NACC = BN > 256 ? 1 : 2;
+  static constexpr int MMA_N = BN > 256 ? BN / 2 : BN;   // N of one tcgen05.mma
+  static constexpr int MMAS = BN / MMA_N;                 // MMAs per k-step
+  static constexpr int B_BOX_ROWS = B_ROWS / MMAS;        // rows of one B TMA box
   static constexpr int NOUT = GEGLU ? BN / 2 : BN;
   // epilogue staging tile [128][SW + 8] fp16, SW output columns per round (a 256-wide tile is staged in two
   // rounds of 128): the 16-byte pad makes a quarter-warp's 16-byte row accesses hit 32 distinct banks
@@ -149,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], TWO ? 2 : 1);  // pairs: both producers arrive on the leader's barrier
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Cfg::NACC; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS);  // pairs: both CTAs' epilogue threads, on the leader
     }
@@ -215,7 +224,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land on this barrier
             else
               mbar_arrive_cluster(&full[stage], 0);
-            tma2_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
+            if constexpr (Cfg::MMAS == 2) {
+              // this CTA's half of each of the two N = 160 MMAs: rows [80 r, 80 r + 80) and [160 + 80 r, ...)
+              const int nt = (w % p.n_tiles) * BN + cta_rank * Cfg::B_BOX_ROWS;
+              tma2_load_2d(sb, &tmB, &full[stage], kb * 64, nt);
+              tma2_load_2d(sb + Cfg::B_BOX_ROWS * 128, &tmB, &full[stage], kb * 64, nt + Cfg::MMA_N);
+            } else {
+              tma2_load_2d(sb, &tmB, &full[stage], kb * 64, n0);
+            }
             if (!p.conv) {
               if (kb < p.kb_split)
                 tma2_load_2d(sa, &tmA, &full[stage], kb * 64, m0);
@@ -257,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {  // pairs: only the leader issues (for both CTAs)
-      constexpr uint32_t idesc = make_idesc_f16(BN, false, TWO ? 256 : 128);
+      constexpr uint32_t idesc = make_idesc_f16(Cfg::MMA_N, false, TWO ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -275,10 +291,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
-            if constexpr (TWO)
+            if constexpr (TWO) {
               umma2_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
+              if constexpr (Cfg::MMAS == 2)
+                umma2_f16(d_tmem + Cfg::MMA_N, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
               umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (TWO)
             umma2_commit(&empty[stage]);
@@ -293,8 +313,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma2_commit(&tfull[as]);
         else
           umma_commit(&tfull[as]);  // accumulator complete
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        if (++as == Cfg::NACC) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -494,8 +516,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         epi_bar();  // staging buffer reusable
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == Cfg::NACC) {
+        as = 0;
+        aphase ^= 1;
+      }
     }
   }
 
@@ -639,7 +663,8 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   // impl 4: one CTA per 128x128 tile (N a multiple of 128; no GEGLU) - for small M, where 128x128 tiles fill the
   //         148 SMs' last wave better than 128x160 or 256x256
   // impl 5: impl 3 with 8 instead of 16 GEGLU epilogue warps (A/B measurements only)
-  const int BN = (impl == 3 || impl == 5) ? 256 : (impl == 4 ? 128 : 160);
+  // impl 6: CTA pairs with 256x320 tiles, one accumulator stage (N a multiple of 320, no GEGLU)
+  const int BN = (impl == 3 || impl == 5) ? 256 : (impl == 4 ? 128 : (impl == 6 ? 320 : 160));
   SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
   SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
   SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
@@ -722,9 +747,10 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
     return check_launch("gemm_simt_kernel");
   }
-  SVDPP_CHECK_ARG(impl == 0 || (impl >= 2 && impl <= 5), "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(impl == 0 || (impl >= 2 && impl <= 6), "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(!(impl == 6 && d->geglu), "gemm: impl 6 has no GEGLU epilogue");
   SVDPP_CHECK_ARG(!(impl == 4 && d->geglu), "gemm: impl 4 has no GEGLU epilogue");
-  const bool two = impl == 2 || impl == 3 || impl == 5;  // CTA pairs (cta_group::2)
+  const bool two = impl == 2 || impl == 3 || impl == 5 || impl == 6;  // CTA pairs (cta_group::2)
 
   CUtensorMap tmA, tmA2, tmB;
   if (!d->conv) {
@@ -767,10 +793,11 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     SVDPP_CHECK_ARG(d->ldw % 8 == 0, "gemm: ldw must be a multiple of 8");
     uint64_t dims[2] = {static_cast<uint64_t>(d->K), static_cast<uint64_t>(d->N)};
     uint64_t str[1] = {static_cast<uint64_t>(d->ldw) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(two ? BN / 2 : BN)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(impl == 6 ? 80 : (two ? BN / 2 : BN))};
     if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
   }
   if (impl == 4) return launch_tc<128, false, false>(tmA, tmA2, tmB, p, stream);
+  if (impl == 6) return launch_tc<320, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 5 && d->geglu) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
   if (impl == 5) return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 3) {

@@ -307,7 +307,11 @@ class NativeUNet(nn.Module):
             return lin.impl
         if self.gemm_impl != 3:
             return self.gemm_impl
-        N = lin.w.shape[0]
+        N, K = lin.w.shape
+        # 256x320 CTA-pair tiles (one accumulator stage) for the N = 320 / 640 layers with a long K loop: measured
+        # +3 % (K = 1280) to +12 % (K = 5760) over 128x160 (tools/gemm_bench.py wide); slower below K = 1280
+        if N in (320, 640) and K >= 1280 and M >= 16384 and not os.environ.get("SVDPP_NO_PAIR320"):
+            return 6
         sms = native.device_info()[2] if self._sms is None else self._sms
         self._sms = sms
         mt = (M + 127) // 128
