@@ -373,6 +373,8 @@ ALL_CHECKS = {
     "bn128_gemm_split": lambda: gemm_linear(M=700, N=512, impl=4, K=384, split=True),
     "bn128_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=128, impl=4),
     "bn128_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=128, impl=4),
+    "pair256_gemm_nstore_partial": lambda: gemm_linear(M=700, N=960, K=320, impl=3, epilogue="full"),
+    "pair256_gemm_nstore_partial_bias": lambda: gemm_linear(M=300, N=1920, K=640, impl=3, epilogue="bias"),
     "pair320_gemm_plain": lambda: gemm_linear(M=512, N=320, K=64, impl=6, epilogue="bias"),
     "pair320_gemm_linear": lambda: gemm_linear(M=300, N=320, K=320, impl=6),
     "pair320_gemm_big": lambda: gemm_linear(M=4000, N=640, K=1280, impl=6),

@@ -65,6 +65,15 @@ if __name__ == "__main__":
         for M, N, K in ((230400, 320, 320), (230400, 320, 1280), (230400, 960, 320), (57600, 640, 2560), (57600, 640, 640),
                         (14400, 1280, 5120), (3600, 1280, 1280)):
             linear_case(M, N, K, (0, 2, 3, 4))
+    if "qkv" in what:    # N = 960 / 1920 padded to a multiple of 256 for the CTA-pair kernel vs 128x160 tiles
+        for M, N, K in ((230400, 960, 320), (57600, 1920, 640)):
+            linear_case(M, N, K, (0,), residual=False)
+            w = torch.zeros((N + 255) // 256 * 256, K, device=DEV, dtype=torch.float16)
+            w[:N] = torch.randn(N, K, device=DEV).half() * K ** -0.5
+            a = [torch.randn(M, K, device=DEV).half() for _ in range(3)]
+            out = [torch.empty(M, N, device=DEV, dtype=torch.float16) for _ in range(3)]
+            ms = timed(lambda i: native.gemm(out[i], a[i], w, n_store=N, impl=3), 3)
+            print(f"linear M={M} N={N}->pad{w.shape[0]} K={K} impl=3: {ms:.4f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
     if "wide" in what:   # the 256x320 pair tile against the one-CTA 128x160 tile on the N = 320 / 640 layers
         for M, N, K in ((230400, 320, 2880), (230400, 320, 960), (230400, 320, 1280), (230400, 320, 640), (57600, 640, 5760),
                         (57600, 640, 2560), (57600, 640, 1920), (57600, 640, 640), (230400, 960, 320), (14400, 1920, 1280)):

@@ -390,8 +390,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               val[k] = make_uint4(0, 0, 0, 0);
               if (m_base + r < p.M) {
                 const __half* src = p.R1 + static_cast<long long>(m_base + r) * p.ldr1 + nout0 + v * 8;
-                if (r_vec) {
+                if (r_vec || ((p.ldr1 & 7) == 0 && nout0 + v * 8 + 8 <= p.n_store)) {
                   val[k] = *reinterpret_cast<const uint4*>(src);
+                } else if (nout0 + v * 8 >= p.n_store) {
+                  // vector entirely beyond the stored columns (N padded to the tile width)
                 } else {
                   __half tmp[8];
                   for (int j = 0; j < 8; ++j) tmp[j] = (nout0 + v * 8 + j < p.n_store) ? src[j] : __float2half(0.f);
@@ -505,8 +507,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (m_base + r < p.M) {
             const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
             __half* dst = p.D + static_cast<long long>(m_base + r) * p.ldd + nout0 + v * 8;
-            if (vec_ok) {
-              *reinterpret_cast<uint4*>(dst) = val;
+            if (vec_ok || ((p.ldd & 7) == 0 && nout0 + v * 8 + 8 <= p.n_store)) {
+              *reinterpret_cast<uint4*>(dst) = val;  // also the whole vectors of a tile that straddles n_store
+            } else if (nout0 + v * 8 >= p.n_store) {
+              // nothing to store
             } else {
               const __half* hv = reinterpret_cast<const __half*>(&val);
               for (int j = 0; j < 8; ++j)

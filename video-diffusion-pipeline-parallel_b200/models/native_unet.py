@@ -211,7 +211,12 @@ class NativeUNet(nn.Module):
     def _fuse_qkv(self, prefix: str) -> _Lin:
         w = torch.cat([self._g(prefix + ".to_q.weight"), self._g(prefix + ".to_k.weight"),
                        self._g(prefix + ".to_v.weight")], dim=0)
-        return _Lin(self._keep(_pad_rows(w)), None, w.shape[0])
+        n = w.shape[0]
+        # 3C = 960 / 1920 are not multiples of 256: padding the rows by <= 7 % buys the 256x256 CTA-pair kernel
+        # (the epilogue stores only the first n columns)
+        if self.gemm_impl == 3 and n % 256 and _ceil_to(n, 256) <= 1.07 * n:
+            return _Lin(self._keep(_pad_rows(w, 256)), None, n)
+        return _Lin(self._keep(_pad_rows(w)), None, n)
 
     def _build_transformer(self, prefix: str, heads: int) -> dict:
         P = dict(heads=heads)
