@@ -1,0 +1,71 @@
+"""CLI modes: the reference's flags and output lines, exercised on CPU/gloo."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, nproc=1, timeout=240):
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    if nproc == 1:
+        cmd = [sys.executable, "-m"] + args
+        env.update(RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", "29612", "-m"] + args
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_simulator_flags_match_reference_defaults():
+    from vdpp_b200.modes.simulator import build_parser
+    a = build_parser().parse_args([])
+    # reference src/modes/simulator.py:35-66
+    assert (a.total_steps, a.latent_channels, a.latent_frames, a.latent_height, a.latent_width) == (28, 8, 8, 32, 32)
+    assert (a.dtype, a.device, a.backend, a.seed, a.latent_batch) == ("fp32", "cpu", "auto", 42, 1)
+
+
+def test_benchmark_flags_match_reference_defaults():
+    from vdpp_b200.modes.benchmark import build_parser
+    a = build_parser().parse_args([])
+    # reference src/modes/benchmark.py:29-62
+    assert (a.total_steps, a.num_samples, a.warmup_samples, a.hidden_channels) == (28, 10, 2, 64)
+    assert (a.latent_channels, a.latent_frames, a.latent_height, a.latent_width) == (4, 14, 40, 72)
+    assert a.model == "dummy" and a.model_id == "stabilityai/stable-video-diffusion-img2vid-xt" and a.guidance_scale is None
+
+
+def test_simulator_two_ranks_gloo_prints_final_norm():
+    r = _run(["src.modes.simulator", "--total-steps", "6", "--latent-channels", "4", "--latent-frames", "3",
+              "--latent-height", "8", "--latent-width", "8"], nproc=2)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Final latent norm:" in r.stderr + r.stdout
+
+
+def test_simulator_rejects_uneven_split_like_the_reference_unless_allowed():
+    base = ["src.modes.simulator", "--total-steps", "5", "--latent-channels", "4", "--latent-frames", "2",
+            "--latent-height", "8", "--latent-width", "8"]
+    bad = _run(base, nproc=2)
+    assert bad.returncode != 0 and "divisible" in (bad.stderr + bad.stdout)
+    ok = _run(base + ["--allow-uneven"], nproc=2)
+    assert ok.returncode == 0 and "Final latent norm:" in ok.stderr + ok.stdout
+
+
+@pytest.mark.parametrize("schedule", ["fixed", "ring"])
+def test_benchmark_mode_prints_benchmark_json(schedule):
+    r = _run(["src.modes.benchmark", "--device", "cpu", "--total-steps", "4", "--num-samples", "4", "--warmup-samples",
+              "2", "--latent-frames", "3", "--latent-height", "8", "--latent-width", "8", "--hidden-channels", "8",
+              "--schedule", schedule], nproc=2)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("BENCHMARK_JSON=")]
+    assert len(line) == 1
+    res = json.loads(line[0].split("=", 1)[1])
+    # keys of reference src/modes/benchmark.py:270-285
+    for k in ("world_size", "total_steps", "steps_per_gpu", "model", "fsdp", "num_samples_measured", "warmup_samples",
+              "latent_shape", "first_sample_time_s", "avg_sample_time_s", "throughput_samples_per_s",
+              "per_sample_times_ms", "peak_memory_gb_per_rank", "max_peak_memory_gb"):
+        assert k in res, k
+    assert res["world_size"] == 2 and res["steps_per_gpu"] == 2 and len(res["per_sample_times_ms"]) == 6
+    assert res["throughput_samples_per_s"] > 0
