@@ -105,6 +105,10 @@ struct GemmCfg {
   // columns leave room for ONE accumulator stage in the 512 TMEM columns, so TMEM reads of the epilogue are not
   // overlapped with the next main loop (stores still are); worth it for K >= 1280.
   static constexpr int NACC = BN > 256 ? 1 : 2;
+  // BN = 320: the two 160-column halves of a tile rotate through THREE TMEM buffers (480 of 512 columns): tile i
+  // uses buffers (2i) % 3 and (2i+1) % 3, so the next tile's MMAs need only the FIRST half of this tile to have
+  // been read by the epilogue, not the whole tile - most of a second accumulator stage without its columns.
+  static constexpr bool ROT3 = BN > 256;
   static constexpr int MMA_N = BN > 256 ? BN / 2 : BN;   // N of one tcgen05.mma
   static constexpr int MMAS = BN / MMA_N;                 // MMAs per k-step
   static constexpr int B_BOX_ROWS = B_ROWS / MMAS;        // rows of one B TMA box
@@ -136,8 +140,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 128);  // [BN] this tile's bias
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 3);
+  __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 192);  // [BN] this tile's bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,10 +162,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], TWO ? 2 : 1);  // pairs: both producers arrive on the leader's barrier
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < Cfg::NACC; ++s) {
-      mbar_init(&tfull[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&tfull[s], 1);
+    for (int s = 0; s < 3; ++s)
       mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS);  // pairs: both CTAs' epilogue threads, on the leader
-    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -278,10 +281,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int w = work_first; w < work_total; w += work_stride) {
-        mbar_wait(&tempty[as], aphase ^ 1, 2);
+      int it = 0;  // tiles done by this CTA pair (ROT3 buffer rotation)
+      for (int w = work_first; w < work_total; w += work_stride, ++it) {
+        uint32_t d_tmem, d_tmem2 = 0;
+        if constexpr (Cfg::ROT3) {
+          const int h0 = 2 * it, h1 = h0 + 1;  // half-tile sequence numbers; buffer = h % 3, its use count = h / 3
+          mbar_wait(&tempty[h0 % 3], ((h0 / 3) & 1) ^ 1, 2);
+          mbar_wait(&tempty[h1 % 3], ((h1 / 3) & 1) ^ 1, 2);
+          d_tmem = tmem_base + (h0 % 3) * Cfg::MMA_N;
+          d_tmem2 = tmem_base + (h1 % 3) * Cfg::MMA_N;
+        } else {
+          mbar_wait(&tempty[as], aphase ^ 1, 2);
+          d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
@@ -294,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (TWO) {
               umma2_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
               if constexpr (Cfg::MMAS == 2)
-                umma2_f16(d_tmem + Cfg::MMA_N, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
+                umma2_f16(d_tmem2, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
                           idesc, (kb | k) != 0 ? 1u : 0u);
             } else {
               umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -309,7 +322,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1;
           }
         }
-        if constexpr (TWO)
+        if constexpr (Cfg::ROT3)
+          umma2_commit(&tfull[it & 1]);
+        else if constexpr (TWO)
           umma2_commit(&tfull[as]);
         else
           umma_commit(&tfull[as]);  // accumulator complete
@@ -339,7 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto epi_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); };
     int as = 0;
     uint32_t aphase = 0;
-    for (int w = work_first; w < work_total; w += work_stride) {
+    int it = 0;
+    for (int w = work_first; w < work_total; w += work_stride, ++it) {
       const int m_tile = m_tile_of(w);
       const int n_tile = w % p.n_tiles;
       const int m_base = m_tile * Cfg::BM;
@@ -359,11 +375,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rv_row = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN;
         }
       }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + as * Cfg::ACC_STRIDE;
+      const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(we * 32) << 16);
       __half* srow = sC + row * Cfg::C_PITCH;
 #pragma unroll 1
       for (int rd = 0; rd < Cfg::ROUNDS; ++rd) {
         const int col0 = rd * SW;                       // first column of this round within the tile
+        // TMEM address of this round's accumulator columns (ROT3: each 160-column half has its own buffer)
+        const int rot_buf = (2 * it + rd) % 3;
+        const uint32_t taddr = Cfg::ROT3 ? taddr_base + rot_buf * Cfg::MMA_N - col0
+                                         : taddr_base + as * Cfg::ACC_STRIDE;
         const int nout0 = n_tile * Cfg::NOUT + col0;    // ... and in the output matrix
         const bool vec_ok = (p.ldd & 7) == 0 && nout0 + SW <= p.n_store;
         // per-image row vector of this thread's row and chunks -> registers, before any wait
@@ -411,7 +431,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         epi_bar();
         if (rd == 0) {
-          mbar_wait(&tfull[as], aphase, 4);
+          if constexpr (Cfg::ROT3)
+            mbar_wait(&tfull[it & 1], (it >> 1) & 1, 4);
+          else
+            mbar_wait(&tfull[as], aphase, 4);
           tc_fence_after();
         }
 #pragma unroll
@@ -494,7 +517,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int q = 0; q < CW / 8; ++q) d4[q] = o4[q];
         }
-        if (rd == Cfg::ROUNDS - 1) {
+        if constexpr (Cfg::ROT3) {
+          tc_fence_before();
+          mbar_arrive_cluster(&tempty[rot_buf], 0);  // this half's buffer is free for the tile after next... or next
+        } else if (rd == Cfg::ROUNDS - 1) {
           tc_fence_before();
           if constexpr (TWO)
             mbar_arrive_cluster(&tempty[as], 0);

@@ -313,9 +313,10 @@ class NativeUNet(nn.Module):
         if self.gemm_impl != 3:
             return self.gemm_impl
         N, K = lin.w.shape
-        # 256x320 CTA-pair tiles (one accumulator stage) for the N = 320 / 640 layers with a long K loop: measured
-        # +3 % (K = 1280) to +12 % (K = 5760) over 128x160 (tools/gemm_bench.py wide); slower below K = 1280
-        if N in (320, 640) and K >= 1280 and M >= 16384 and not os.environ.get("SVDPP_NO_PAIR320"):
+        # 256x320 CTA-pair tiles (halves rotating through three TMEM buffers) for the N = 320 / 640 layers: measured
+        # against 128x160 in conv mode (tools/gemm_once.py): K = 960 +11 %, 1920 +28 %, 2880 +23 %, 5760 +36 %;
+        # K = 640 -6 %, so the narrow tile stays below K = 960
+        if N in (320, 640) and K >= 960 and M >= 16384 and not os.environ.get("SVDPP_NO_PAIR320"):
             return 6
         sms = native.device_info()[2] if self._sms is None else self._sms
         self._sms = sms
