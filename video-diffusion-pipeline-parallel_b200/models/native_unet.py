@@ -301,33 +301,33 @@ class NativeUNet(nn.Module):
         return native.groupnorm_silu(out, x1, norm[0], norm[1], n_img=n_img, HW=HW, eps=eps, silu=silu, x2=x2,
                                      frames_per_stat=fps, workspace=self._gn_ws)
 
-    # relative per-SM throughput of the tile shapes on large problems (measured: 256x256 CTA pairs +15-25 % over
-    # 128x160; 128x128 a little below it)
-    _TILE_SPEED = {3: 1.2, 0: 1.0, 4: 0.92}
+    # relative per-SM throughput of the tile shapes on many-wave problems (measured: 256x256 CTA pairs +15-25 % over
+    # 128x160; 256x320 pairs a little below 256x256 where both apply; 128x128 below 128x160)
+    _TILE_SPEED = {3: 1.2, 6: 1.15, 0: 1.0, 4: 0.8}
 
     def _impl(self, lin: _Lin, M: int = 1 << 30) -> int:
-        """Tile shape for one GEMM: the packed layout fixes it for GEGLU; otherwise, in auto mode (3), the
-        candidate whose last wave over the 148 SMs wastes least (matters at M = 3600, the 9x16 level)."""
+        """Tile shape for one GEMM.  The packed layout fixes it for GEGLU; otherwise, in auto mode (3), the candidate
+        with the smallest estimated time = waves over the 148 SMs x tile area / relative speed.  The wave count
+        decides at small M: at M = 3600 (the 9x16 level) N = 1280 is 75 pair tiles of 256x256 - one more than the 74
+        CTA pairs, i.e. two waves - but 60 tiles of 256x320: 502 -> 875 TFLOP/s on the 3x3 convs there."""
         if lin.impl is not None:
             return lin.impl
         if self.gemm_impl != 3:
             return self.gemm_impl
         N, K = lin.w.shape
-        # 256x320 CTA-pair tiles (halves rotating through three TMEM buffers) for the N = 320 / 640 layers: measured
-        # against 128x160 in conv mode (tools/gemm_once.py): K = 960 +11 %, 1920 +28 %, 2880 +23 %, 5760 +36 %;
-        # K = 640 -6 %, so the narrow tile stays below K = 960
-        if N in (320, 640) and K >= 960 and M >= 16384 and not os.environ.get("SVDPP_NO_PAIR320"):
-            return 6
         sms = native.device_info()[2] if self._sms is None else self._sms
         self._sms = sms
         mt = (M + 127) // 128
         best, best_t = 0, None
-        for impl, bn, per_cta in ((3, 256, 128 * 256), (0, 160, 128 * 160), (4, 128, 128 * 128)):
+        for impl, bn, pair in ((3, 256, True), (6, 320, True), (0, 160, False), (4, 128, False)):
             if N % bn or (impl == 4 and os.environ.get("SVDPP_NO_BN128")):
                 continue
-            work = ((mt + 1) // 2) * (N // bn) if impl == 3 else mt * (N // bn)
-            slots = sms // 2 if impl == 3 else sms
-            t = -(-work // slots) * per_cta / self._TILE_SPEED[impl]
+            # 256x320: three rotating TMEM buffers instead of two full stages - loses below K = 960 (measured)
+            if impl == 6 and (K < 960 or os.environ.get("SVDPP_NO_PAIR320")):
+                continue
+            work = ((mt + 1) // 2) * (N // bn) if pair else mt * (N // bn)
+            slots = sms // 2 if pair else sms
+            t = -(-work // slots) * 128 * bn / self._TILE_SPEED[impl]
             if best_t is None or t < best_t:
                 best, best_t = impl, t
         return best
