@@ -97,7 +97,12 @@ struct GemmCfg {
   static constexpr int B_ROWS = TWO ? BN / 2 : BN;  // B rows this CTA loads
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (TWO && BN <= 160) ? 6 : 5;
+  // GROUPS = 2 (the 16-warp GEGLU epilogue): two independent groups of 8 epilogue warps, each with its own TMEM
+  // stage, staging tile, bias tile and named barrier, take alternate tiles - the barrier and TMEM-load stalls of one
+  // group are covered by the other group's arithmetic instead of idling all 16 warps (ncu: 26 % of the K = 320
+  // GEGLU's samples sat on the epilogue's named barrier).  Costs one pipeline stage of smem.
+  static constexpr int GROUPS = (GEGLU && BN == 256 && (EW_ ? EW_ : 16) == 16) ? 2 : 1;
+  static constexpr int STAGES = (TWO && BN <= 160) ? 6 : (GROUPS == 2 ? 4 : 5);
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
   // BN = 320 (CTA pairs only): the whole N = 320 of the level-0 layers in one 256 x 320 pair tile, issued as two
   // N = 160 MMAs per k-step.  Per CTA and k-block 36 KB come from L2 for 5.2 MFLOP (145 FLOP/B against 71 for the
@@ -119,7 +124,7 @@ struct GemmCfg {
   static constexpr int SW = NOUT / ROUNDS;
   static constexpr int C_PITCH = SW + 8;
   static constexpr int C_BYTES = BM * C_PITCH * 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 1024 /*barriers + bias tile*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GROUPS * C_BYTES + 1024 /*align*/ + 2048 /*barriers + bias tiles*/;
   // Epilogue warps: the GEGLU epilogue (two accumulators, exact GELU, fp16 roundings per output) needs about as
   // many issue slots per tile as the K = 320 main loop has cycles; with 8 warps (2 per scheduler) dependency
   // stalls made it the bound.  It uses few registers, so the 256-wide variant runs 16 epilogue warps.
@@ -136,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __half* sC = reinterpret_cast<__half*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::C_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::GROUPS * Cfg::C_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -164,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) mbar_init(&tfull[s], 1);
     for (int s = 0; s < 3; ++s)
-      mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS);  // pairs: both CTAs' epilogue threads, on the leader
+      mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS / Cfg::GROUPS);  // pairs: both CTAs' epilogue threads, on the leader
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -341,21 +346,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // buffer (the TMEM stage is released after the last round), (3) coalesced copy of the staging buffer
     // to global.  Thread = accumulator row; the two warps of a lane quarter take alternate column chunks.
     const int we = warp & 3;          // the TMEM lane quarter this warp may read (warp % 4)
-    constexpr int EW = Cfg::EPI_WARPS, ET = Cfg::EPI_THREADS, WPQ = EW / 4;  // WPQ warps share a TMEM lane quarter
-    const int half = (warp - 4) >> 2;  // which of the quarter's WPQ warps: takes column chunks half, half + WPQ, ...
+    constexpr int EW = Cfg::EPI_WARPS / Cfg::GROUPS, ET = EW * 32, WPQ = EW / 4;  // per group; WPQ warps share a lane quarter
+    const int grp = Cfg::GROUPS == 2 ? (warp - 4) / EW : 0;  // epilogue group: takes tiles grp, grp + GROUPS, ...
+    const int half = ((warp - 4) % EW) >> 2;  // which of the quarter's WPQ warps: takes column chunks half, half + WPQ, ...
     const int row = we * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..ET-1
+    const int et = (threadIdx.x - 128) % ET;  // 0..ET-1 within the group
+    sC += grp * (Cfg::C_BYTES / 2);
+    sBias += grp * BN;
     constexpr int SW = Cfg::SW;
     constexpr int VPR = SW / 8;         // 16-byte vectors per staged row
     constexpr int CW = GEGLU ? 8 : 16;  // columns per chunk
     constexpr int NCH = SW / CW / WPQ;  // chunks per warp and round
     constexpr int NV = Cfg::BM * VPR / ET;  // staged vectors per thread
     static_assert(Cfg::BM * VPR % ET == 0 && (SW / CW) % WPQ == 0, "epilogue work split");
-    auto epi_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); };
-    int as = 0;
+    auto epi_bar = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(ET) : "memory"); };
+    int as = Cfg::GROUPS == 2 ? grp : 0;  // with two groups each owns one TMEM stage
     uint32_t aphase = 0;
-    int it = 0;
-    for (int w = work_first; w < work_total; w += work_stride, ++it) {
+    int it = grp;
+    for (int w = work_first + grp * work_stride; w < work_total; w += Cfg::GROUPS * work_stride, it += Cfg::GROUPS) {
       const int m_tile = m_tile_of(w);
       const int n_tile = w % p.n_tiles;
       const int m_base = m_tile * Cfg::BM;
@@ -546,7 +554,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         epi_bar();  // staging buffer reusable
       }
-      if (++as == Cfg::NACC) {
+      if constexpr (Cfg::GROUPS == 2) {
+        aphase ^= 1;  // this group's stage completes once per tile of the group
+      } else if (++as == Cfg::NACC) {
         as = 0;
         aphase ^= 1;
       }
@@ -831,7 +841,8 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   if (impl == 5 && d->geglu) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
   if (impl == 5) return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 3) {
-    // 16 epilogue warps pay off only where the epilogue outweighs the main loop (K = 320: +5 %; K >= 640: -1.5 %)
+    // 16 epilogue warps in two independent groups pay off only where the epilogue outweighs the main loop
+    // (K = 320: 863 -> 957 TFLOP/s; K >= 640: no gain)
     if (d->geglu && d->K > 384) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
     if (d->geglu) return launch_tc<256, true, true>(tmA, tmA2, tmB, p, stream);
     return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);
