@@ -69,3 +69,19 @@ def test_benchmark_mode_prints_benchmark_json(schedule):
         assert k in res, k
     assert res["world_size"] == 2 and res["steps_per_gpu"] == 2 and len(res["per_sample_times_ms"]) == 6
     assert res["throughput_samples_per_s"] > 0
+
+
+def test_data_parallel_mode_prints_benchmark_json():
+    r = _run(["src.modes.benchmark_data_parallel", "--device", "cpu", "--total-steps", "3", "--num-samples", "4",
+              "--warmup-samples", "1", "--latent-frames", "3", "--latent-height", "8", "--latent-width", "8",
+              "--hidden-channels", "8"], nproc=2)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("BENCHMARK_JSON=")]
+    assert len(line) == 1
+    res = json.loads(line[0].split("=", 1)[1])
+    # keys of reference src/modes/benchmark_data_parallel.py:233-248
+    for k in ("mode", "world_size", "total_steps", "steps_per_gpu", "model", "num_samples_measured", "warmup_samples",
+              "samples_per_rank", "latent_shape", "first_sample_time_s", "avg_sample_time_s", "throughput_samples_per_s",
+              "wall_clock_s", "per_sample_times_ms"):
+        assert k in res, k
+    assert res["mode"] == "data_parallel" and res["num_samples_measured"] == 4 and res["samples_per_rank"] == 2

@@ -16,6 +16,7 @@ ap.add_argument("--N", type=int, default=320)
 ap.add_argument("--K", type=int, default=2880)
 ap.add_argument("--impl", type=int, default=0)
 ap.add_argument("--iters", type=int, default=4)
+ap.add_argument("--no-res", action="store_true", help="no residual input (e.g. the qkv projection)")
 ap.add_argument("--temporal", action="store_true", help="with --conv: the (3,1,1) temporal conv (K = 3*C) instead of 3x3")
 ap.add_argument("--conv", type=int, nargs=5, default=None, metavar=("B", "F", "H", "W", "C"),
                 help="3x3 conv over a channels-last activation instead of a plain matrix (K = 9*C)")
@@ -29,7 +30,7 @@ w = torch.zeros(npad, a.K, device="cuda", dtype=torch.float16)
 w[:a.N] = torch.randn(a.N, a.K, device="cuda").half() * a.K ** -0.5
 b = torch.zeros(npad, device="cuda", dtype=torch.float16)
 xs = [torch.randn(a.M, a.conv[4] if a.conv else a.K, device="cuda").half() for _ in range(2)]
-r = torch.randn(a.M, a.N, device="cuda").half()
+r = None if a.no_res else torch.randn(a.M, a.N, device="cuda").half()
 out = torch.empty(a.M, a.N, device="cuda", dtype=torch.float16)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(a.iters):
