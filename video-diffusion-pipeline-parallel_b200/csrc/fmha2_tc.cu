@@ -86,8 +86,8 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 // Measured dead end: evaluating every fourth (or eighth) exponential with a degree-3 polynomial on the FMA pipe
-// (poly3_exp2) to relieve the MUFU pipe was SLOWER (774 vs 799 TFLOP/s): the softmax warps run out of issue
-// slots before the MUFU pipe (73 % busy) saturates.
+// (poly3_exp2) to relieve the MUFU pipe was SLOWER (774 vs 799 TFLOP/s; with the packed-arithmetic loop 750 vs 805):
+// the softmax warps run out of issue slots before the MUFU pipe (73 % busy) saturates.
 template <int SPLIT>
 __global__ void __launch_bounds__(A2Cfg<SPLIT>::THREADS, 1)
 attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
