@@ -37,14 +37,14 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  * GEMM / implicit-GEMM convolution with fused epilogue (tcgen05 + TMEM + TMA).
  *   acc[m, n] = sum_k A[m, k] * Wt[n, k]                         (fp16 inputs, fp32 accumulate)
  *   y[m, n]   = alpha * (acc + bias[n] + rowvec[rv(m), n]) + beta1 * R1[m, n] + beta2 * R2[m, n]
- *   geglu: Wt rows are interleaved per 160-row tile as [80 value | 80 gate];
+ *   geglu: Wt rows are interleaved per tile as [half value | half gate] (80 + 80 for 160-wide tiles, 128 + 128 for impl 3);
  *          D[m, j] = y_value[m, j] * gelu(y_gate[m, j]),  D has N/2 columns.
  * A is either a plain matrix (optionally the K-concatenation [A | A2], split at K1), or, in conv
  * mode, the channels-last activation [cB, cF, cH, cW, cC] read through `ntaps` shifted windows
  * (tap t contributes K-slice [t*cC, (t+1)*cC); out-of-range pixels/frames read as zero).
  * Replaces: nn.Linear / Conv2d 3x3 / Conv3d (3,1,1) / 1x1 shortcut / GEGLU inside
  * UNetSpatioTemporalConditionModel (called at svd_unet.py:389-395).
- * Requirements: K % 64 == 0, K1 % 64 == 0, N % 160 == 0 (pad Wt), 16-byte aligned rows.
+ * Requirements: K % 64 == 0, K1 % 64 == 0, N a multiple of the tile width (pad Wt), 16-byte aligned rows.
  * -------------------------------------------------------------------------------------------*/
 typedef struct svdpp_gemm_desc {
   int32_t M, N, K;
@@ -66,8 +66,12 @@ typedef struct svdpp_gemm_desc {
   int32_t n_store;                        /* store columns n < n_store (after geglu halving) */
 } svdpp_gemm_desc;
 
-/* impl: 0 = tcgen05 kernel, one CTA per tile; 2 = tcgen05 kernel with CTA pairs (cta_group::2, 256-row tiles);
- *       1 = plain CUDA-core kernel (slow; bring-up cross-check) */
+/* impl selects the tile shape of the tcgen05 kernel (Wt must be padded to a multiple of the tile's N):
+ *   0 = one CTA per 128x160 tile           4 = one CTA per 128x128 tile (no GEGLU)
+ *   2 = CTA pair (cta_group::2), 256x160   3 = CTA pair, 256x256 (GEGLU rows interleaved [128 value | 128 gate])
+ *   6 = CTA pair, 256x320 as two N=160 MMAs per k-step, halves rotating through three TMEM buffers (no GEGLU)
+ *   5 = impl 3 with 8 instead of 16 GEGLU epilogue warps (A/B measurements)
+ *   1 = plain CUDA-core kernel (slow; bring-up cross-check) */
 int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
