@@ -41,7 +41,8 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *          D[m, j] = y_value[m, j] * gelu(y_gate[m, j]),  D has N/2 columns.
  * A is either a plain matrix (optionally the K-concatenation [A | A2], split at K1), or, in conv
  * mode, the channels-last activation [cB, cF, cH, cW, cC] read through `ntaps` shifted windows
- * (tap t contributes K-slice [t*cC, (t+1)*cC); out-of-range pixels/frames read as zero).
+ * (tap t contributes K-slice [t*cC, (t+1)*cC); out-of-range pixels/frames read as zero); with conv_stride = 2 the
+ * windows are strided (the down-sampling Conv2d 3x3 stride 2 pad 1), still without materialising im2col.
  * Replaces: nn.Linear / Conv2d 3x3 / Conv3d (3,1,1) / 1x1 shortcut / GEGLU inside
  * UNetSpatioTemporalConditionModel (called at svd_unet.py:389-395).
  * Requirements: K % 64 == 0, K1 % 64 == 0, N a multiple of the tile width (pad Wt), 16-byte aligned rows.
@@ -64,6 +65,10 @@ typedef struct svdpp_gemm_desc {
   int32_t geglu;
   void* D;         int64_t ldd;
   int32_t n_store;                        /* store columns n < n_store (after geglu halving) */
+  /* strided convolution (conv mode): output pixel (h, w) reads input (h*conv_stride + dh, w*conv_stride + dw).
+   * cH, cW above are then the OUTPUT extent (cB*cF*cH*cW == M) and cHin, cWin the input extent.
+   * conv_stride 0 or 1: plain convolution, cHin/cWin ignored. */
+  int32_t conv_stride, cHin, cWin;
 } svdpp_gemm_desc;
 
 /* impl selects the tile shape of the tcgen05 kernel (Wt must be padded to a multiple of the tile's N):

@@ -100,6 +100,21 @@ def conv3x3(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
     return _cmp(out, ref.reshape(-1, Cout))
 
 
+def conv3x3_stride2(B=1, Fr=2, H=12, W=64, C=64, Cout=96, impl=0):
+    """Down-sampling Conv2d 3x3 stride 2 pad 1 through the strided-window path (no im2col)."""
+    x = _rand(B * Fr, H, W, C, seed=1)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    b = _rand(Cout, seed=3)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    wk = _pad_n(w.permute(0, 2, 3, 1).reshape(Cout, -1), _bn(impl))
+    out = torch.full((B * Fr * Ho * Wo, Cout), float("nan"), device=DEV, dtype=torch.float16)
+    native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, Ho, Wo, C), taps=native.TAPS_3X3,
+                n_store=Cout, impl=impl, conv_stride=2, conv_in_hw=(H, W))
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    return _cmp(out, ref.reshape(-1, Cout))
+
+
 def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
     x = _rand(B, Fr, H, W, C, seed=1)
     w = _rand(C, C, 3, 1, 1, scale=(3 * C) ** -0.5, seed=2)
@@ -352,6 +367,12 @@ ALL_CHECKS = {
     "tc_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=160, impl=0),
     "tc_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=64, impl=0),
     "tc_conv_temporal": lambda: conv_temporal(impl=0),
+    "simt_conv3x3_stride2": lambda: conv3x3_stride2(impl=1),
+    "tc_conv3x3_stride2_w32": lambda: conv3x3_stride2(impl=0),
+    "tc_conv3x3_stride2_w16_odd": lambda: conv3x3_stride2(B=1, Fr=3, H=9, W=32, C=64, Cout=64, impl=0),
+    "tc_conv3x3_stride2_w128": lambda: conv3x3_stride2(B=1, Fr=1, H=6, W=256, C=64, Cout=160, impl=0),
+    "pair256_conv3x3_stride2": lambda: conv3x3_stride2(B=2, Fr=2, H=16, W=64, C=128, Cout=256, impl=3),
+    "pair320_conv3x3_stride2": lambda: conv3x3_stride2(B=2, Fr=2, H=16, W=64, C=128, Cout=320, impl=6),
     "pair_gemm_plain": lambda: gemm_linear(M=256, N=160, K=64, impl=2, epilogue="bias"),
     "pair_gemm_linear": lambda: gemm_linear(impl=2),
     "pair_gemm_big": lambda: gemm_linear(M=4000, N=640, K=1280, impl=2),

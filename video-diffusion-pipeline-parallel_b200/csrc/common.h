@@ -42,7 +42,9 @@ int num_sms();
 
 // fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first;
 // strides_bytes has rank-1 entries (dimension 0 is contiguous).
+// elem_strides (optional): traversal stride per dimension; a box of extent box[i] then loads
+// ceil(box[i] / elem_strides[i]) elements (used for the stride-2 down-sampling convolutions).
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box);
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 }  // namespace svdpp

@@ -21,7 +21,7 @@ namespace svdpp {
 struct GemmParams {
   int M, N;
   int num_kb, kb_split;
-  int conv, cF, cH, cW, cpk, nrows, bw;
+  int conv, cF, cH, cW, cpk, nrows, bw, cstride;
   int8_t taps[SVDPP_MAX_TAPS][4];
   const __half* bias;
   const __half* rowvec;
@@ -261,11 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.conv) {
           if (lane < p.nrows) {
             if constexpr (TWO)
-              tma2_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
-                           ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+              tma2_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw * p.cstride + p.taps[tap][0],
+                           ch * p.cstride + p.taps[tap][1], cf + p.taps[tap][2], cb);
             else
-              tma_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw + p.taps[tap][0],
-                          ch + p.taps[tap][1], cf + p.taps[tap][2], cb);
+              tma_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw * p.cstride + p.taps[tap][0],
+                          ch * p.cstride + p.taps[tap][1], cf + p.taps[tap][2], cb);
           }
           if (++kc == p.cpk) {
             kc = 0;
@@ -586,7 +586,7 @@ struct SimtParams {
   long long lda;
   const __half* A2;
   long long lda2;
-  int conv, cB, cF, cH, cW, cC, ntaps;
+  int conv, cB, cF, cH, cW, cC, ntaps, cstride, cHin, cWin;
   int8_t taps[SVDPP_MAX_TAPS][4];
   const __half* Wt;
   long long ldw;
@@ -613,9 +613,9 @@ __device__ __forceinline__ float simt_dot(const SimtParams& p, int m, int n) {
     int f = img % p.cF;
     int b = img / p.cF;
     for (int t = 0; t < p.ntaps; ++t) {
-      int ww = w + p.taps[t][0], hh = h + p.taps[t][1], ff = f + p.taps[t][2];
-      if (ww < 0 || ww >= p.cW || hh < 0 || hh >= p.cH || ff < 0 || ff >= p.cF) continue;
-      const __half* src = p.A + ((((static_cast<long long>(b) * p.cF + ff) * p.cH + hh) * p.cW) + ww) * p.cC;
+      int ww = w * p.cstride + p.taps[t][0], hh = h * p.cstride + p.taps[t][1], ff = f + p.taps[t][2];
+      if (ww < 0 || ww >= p.cWin || hh < 0 || hh >= p.cHin || ff < 0 || ff >= p.cF) continue;
+      const __half* src = p.A + ((((static_cast<long long>(b) * p.cF + ff) * p.cHin + hh) * p.cWin) + ww) * p.cC;
       const __half* wk = wrow + t * p.cC;
       for (int c = 0; c < p.cC; ++c) acc += __half2float(src[c]) * __half2float(wk[c]);
     }
@@ -752,6 +752,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     p.cF = d->cF;
     p.cH = d->cH;
     p.cW = d->cW;
+    p.cstride = d->conv_stride > 1 ? d->conv_stride : 1;
+    SVDPP_CHECK_ARG(p.cstride <= 2, "gemm: conv_stride=%d unsupported", d->conv_stride);
+    SVDPP_CHECK_ARG(p.cstride == 1 || (d->cHin >= d->cH && d->cWin >= d->cW), "gemm: strided conv needs cHin/cWin");
   }
 
   if (impl == 3 || impl == 5) {
@@ -772,6 +775,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     sp.cF = d->cF;
     sp.cH = d->cH;
     sp.cW = d->cW;
+    sp.cstride = d->conv_stride > 1 ? d->conv_stride : 1;
+    sp.cHin = sp.cstride > 1 ? d->cHin : d->cH;
+    sp.cWin = sp.cstride > 1 ? d->cWin : d->cW;
     sp.cC = d->cC;
     sp.ntaps = d->ntaps;
     for (int t = 0; t < SVDPP_MAX_TAPS; ++t)
@@ -818,15 +824,21 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     p.bw = W < 128 ? W : 128;
     p.nrows = 128 / p.bw;
     p.cpk = d->cC / 64;
-    uint64_t dims[5] = {static_cast<uint64_t>(d->cC), static_cast<uint64_t>(d->cW), static_cast<uint64_t>(d->cH),
+    const int s = p.cstride;
+    const int Win = s > 1 ? d->cWin : d->cW, Hin = s > 1 ? d->cHin : d->cH;
+    uint64_t dims[5] = {static_cast<uint64_t>(d->cC), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                         static_cast<uint64_t>(d->cF), static_cast<uint64_t>(d->cB)};
     uint64_t str[4];
     str[0] = static_cast<uint64_t>(d->cC) * 2;
-    str[1] = str[0] * d->cW;
-    str[2] = str[1] * d->cH;
+    str[1] = str[0] * Win;
+    str[2] = str[1] * Hin;
     str[3] = str[2] * d->cF;
-    uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), 1, 1, 1};
-    if (encode_tmap_f16(&tmA, d->A, 5, dims, str, box)) return -5;
+    // strided windows: the box spans (bw - 1) * s + 1 input pixels and is traversed with element stride s, which
+    // loads exactly bw pixels
+    uint32_t box[5] = {64, static_cast<uint32_t>((p.bw - 1) * s + 1), 1, 1, 1};
+    uint32_t estr[5] = {1, static_cast<uint32_t>(s), 1, 1, 1};
+    SVDPP_CHECK_ARG(box[1] <= 256, "gemm: strided conv box too wide");
+    if (encode_tmap_f16(&tmA, d->A, 5, dims, str, box, s > 1 ? estr : nullptr)) return -5;
     tmA2 = tmA;
   }
   {

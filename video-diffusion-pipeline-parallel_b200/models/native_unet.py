@@ -462,9 +462,16 @@ class NativeUNet(nn.Module):
             if blk["down"] is not None:
                 C = x.shape[1]
                 ho, wo = (h + 1) // 2, (w + 1) // 2
-                cols = self._new(B * F * ho * wo, 9 * C)
-                native.im2col(cols, x, B=B, F=F, H=h, W=w, Cc=C, Ho=ho, Wo=wo, stride=2, taps=TAPS_3X3)
-                x = self._linear(cols, blk["down"])
+                lin = blk["down"]
+                if window_path_ok(wo, C):
+                    # Conv2d 3x3 stride 2 pad 1 as strided TMA windows (element stride 2 along W, rows 2*ho + dh)
+                    x = native.gemm(self._new(B * F * ho * wo, lin.n), x, lin.w, bias=lin.b, conv_dims=(B, F, ho, wo, C),
+                                    taps=TAPS_3X3, n_store=lin.n, impl=self._impl(lin, B * F * ho * wo), conv_stride=2,
+                                    conv_in_hw=(h, w))
+                else:
+                    cols = self._new(B * F * ho * wo, 9 * C)
+                    native.im2col(cols, x, B=B, F=F, H=h, W=w, Cc=C, Ho=ho, Wo=wo, stride=2, taps=TAPS_3X3)
+                    x = self._linear(cols, lin)
                 h, w = ho, wo
                 skips.append(x)
         x = self._resblock(x, None, self.mid["res"][0], tembs, B, F, h, w)

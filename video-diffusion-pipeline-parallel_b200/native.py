@@ -50,6 +50,7 @@ class GemmDesc(C.Structure):
         ("geglu", C.c_int32),
         ("D", C.c_void_p), ("ldd", C.c_int64),
         ("n_store", C.c_int32),
+        ("conv_stride", C.c_int32), ("cHin", C.c_int32), ("cWin", C.c_int32),
     ]
 
 
@@ -171,11 +172,13 @@ def _fill_taps(desc: GemmDesc, taps: Sequence[Tuple[int, int, int]]) -> None:
 def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=None,
          conv_dims: Optional[Tuple[int, int, int, int, int]] = None, taps=None,
          rowvec=None, rv_hw=1, rv_div=1, rv_mod=0, r1=None, beta1=1.0, r2=None, beta2=1.0, alpha=1.0,
-         geglu=False, n_store=0, impl=0) -> torch.Tensor:
+         geglu=False, n_store=0, impl=0, conv_stride: int = 1,
+         conv_in_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """``out = epilogue(A @ w.T)``; see ``svdpp_gemm_desc`` in include/svdpp.h.
 
     ``a``: [M, K] (row stride may exceed K) or, with ``conv_dims=(B,F,H,W,C)``, the contiguous
-    channels-last activation.  ``w``: [N, K] fp16, N a multiple of 160 (GEGLU-interleaved if geglu).
+    channels-last activation.  ``w``: [N, K] fp16, N a multiple of the tile width (GEGLU-interleaved if geglu).
+    ``conv_stride=2`` with ``conv_in_hw=(Hin, Win)``: strided windows (conv_dims then holds the OUTPUT H, W).
     """
     lib = load()
     d = GemmDesc()
@@ -193,6 +196,10 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
         if not a.is_contiguous():
             raise NativeError("conv-mode activation must be contiguous")
         d.A, d.lda = a.data_ptr(), C_
+        if conv_stride > 1:
+            if conv_in_hw is None:
+                raise NativeError("strided conv needs conv_in_hw=(Hin, Win)")
+            d.conv_stride, d.cHin, d.cWin = conv_stride, conv_in_hw[0], conv_in_hw[1]
     else:
         d.conv = 0
         d.M = a.shape[0]
