@@ -69,6 +69,11 @@ typedef struct svdpp_gemm_desc {
    * cH, cW above are then the OUTPUT extent (cB*cF*cH*cW == M) and cHin, cWin the input extent.
    * conv_stride 0 or 1: plain convolution, cHin/cWin ignored. */
   int32_t conv_stride, cHin, cWin;
+  /* sub-pixel output map (conv mode): out_up = 2 stores GEMM row (img, h, w) of the cH x cW grid at pixel
+   * (2h + out_up_y, 2w + out_up_x) of a (2 cH) x (2 cW) output image (D has cB*cF*4*cH*cW rows).  Used to run
+   * "nearest-neighbour 2x upsample + Conv2d 3x3" as four 2x2-tap convolutions on the low-resolution input, one per
+   * output parity, with pre-summed weights: 4/9 of the FLOPs and no upsampled tensor.  0 or 1: off. */
+  int32_t out_up, out_up_y, out_up_x;
 } svdpp_gemm_desc;
 
 /* impl selects the tile shape of the tcgen05 kernel (Wt must be padded to a multiple of the tile's N):

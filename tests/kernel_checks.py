@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 import vdpp_b200  # noqa: F401
 from vdpp_b200 import native
-from vdpp_b200.models.native_unet import interleave_geglu
+from vdpp_b200.models.native_unet import interleave_geglu, subpixel_taps, subpixel_weight
 
 DEV = "cuda"
 
@@ -111,6 +111,23 @@ def conv3x3_stride2(B=1, Fr=2, H=12, W=64, C=64, Cout=96, impl=0):
     native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, Ho, Wo, C), taps=native.TAPS_3X3,
                 n_store=Cout, impl=impl, conv_stride=2, conv_in_hw=(H, W))
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    return _cmp(out, ref.reshape(-1, Cout))
+
+
+def conv_up2x(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
+    """Nearest 2x upsample + Conv2d 3x3 as four parity convolutions with the sub-pixel output map."""
+    x = _rand(B * Fr, H, W, C, seed=1)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    b = _rand(Cout, seed=3)
+    out = torch.full((B * Fr * 4 * H * W, Cout), float("nan"), device=DEV, dtype=torch.float16)
+    for py in (0, 1):
+        for px in (0, 1):
+            wk = _pad_n(subpixel_weight(w, py, px), _bn(impl))
+            native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, H, W, C),
+                        taps=subpixel_taps(py, px), n_store=Cout, impl=impl, out_up=(2, py, px))
+    up = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
     return _cmp(out, ref.reshape(-1, Cout))
 
@@ -367,6 +384,11 @@ ALL_CHECKS = {
     "tc_conv3x3_w128": lambda: conv3x3(B=1, Fr=2, H=3, W=128, C=128, Cout=160, impl=0),
     "tc_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=64, impl=0),
     "tc_conv_temporal": lambda: conv_temporal(impl=0),
+    "simt_conv_up2x": lambda: conv_up2x(impl=1),
+    "tc_conv_up2x_w32": lambda: conv_up2x(impl=0),
+    "tc_conv_up2x_w16": lambda: conv_up2x(B=1, Fr=3, H=9, W=16, C=64, Cout=64, impl=0),
+    "pair256_conv_up2x": lambda: conv_up2x(B=2, Fr=2, H=8, W=32, C=128, Cout=256, impl=3),
+    "pair320_conv_up2x": lambda: conv_up2x(B=2, Fr=2, H=8, W=64, C=128, Cout=320, impl=6),
     "simt_conv3x3_stride2": lambda: conv3x3_stride2(impl=1),
     "tc_conv3x3_stride2_w32": lambda: conv3x3_stride2(impl=0),
     "tc_conv3x3_stride2_w16_odd": lambda: conv3x3_stride2(B=1, Fr=3, H=9, W=32, C=64, Cout=64, impl=0),

@@ -39,6 +39,9 @@ struct GemmParams {
   int n_store;
   int m_tiles, n_tiles;
   int prefetch_r1;  // producer warp pulls the residual tile into L2 one main loop ahead of the epilogue
+  // sub-pixel output map (conv mode, up > 1): GEMM row m = pixel (img, h, w) of the cH x cW grid is stored at pixel
+  // (up*h + up_y, up*w + up_x) of the (up*cH) x (up*cW) output image
+  int up, up_y, up_x;
 };
 
 // Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
@@ -84,6 +87,16 @@ __device__ __forceinline__ void load8(const __half* p, float (&o)[8]) {
     o[2 * i] = f.x;
     o[2 * i + 1] = f.y;
   }
+}
+
+// Output row of GEMM row m (identity unless the sub-pixel map is on)
+__device__ __forceinline__ long long out_row(const GemmParams& p, int m) {
+  if (p.up <= 1) return m;
+  const int w = m % p.cW;
+  const int r = m / p.cW;
+  const int h = r % p.cH;
+  const long long img = r / p.cH;
+  return (img * (p.up * p.cH) + p.up * h + p.up_y) * (p.up * p.cW) + p.up * w + p.up_x;
 }
 
 // TWO: CTA pairs (cta_group::2).  The pair computes a 256 x BN tile: each CTA loads its own 128 rows of A
@@ -540,7 +553,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int r = i / VPR, v = i - r * VPR;
           if (m_base + r < p.M) {
             const uint4 val = *reinterpret_cast<const uint4*>(sC + r * Cfg::C_PITCH + v * 8);
-            __half* dst = p.D + static_cast<long long>(m_base + r) * p.ldd + nout0 + v * 8;
+            __half* dst = p.D + out_row(p, m_base + r) * p.ldd + nout0 + v * 8;
             if (vec_ok || ((p.ldd & 7) == 0 && nout0 + v * 8 + 8 <= p.n_store)) {
               *reinterpret_cast<uint4*>(dst) = val;  // also the whole vectors of a tile that straddles n_store
             } else if (nout0 + v * 8 >= p.n_store) {
@@ -654,7 +667,7 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
     if (e.R2) y += e.beta2 * __half2float(e.R2[static_cast<long long>(m) * e.ldr2 + nout]);
     o = __float2half_rn(y);
   }
-  e.D[static_cast<long long>(m) * e.ldd + nout] = o;
+  e.D[out_row(e, m) * e.ldd + nout] = o;
 }
 
 template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
@@ -752,6 +765,11 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     p.cF = d->cF;
     p.cH = d->cH;
     p.cW = d->cW;
+    p.up = d->out_up > 1 ? d->out_up : 1;
+    p.up_y = d->out_up_y;
+    p.up_x = d->out_up_x;
+    SVDPP_CHECK_ARG(p.up <= 2 && p.up_y >= 0 && p.up_y < p.up && p.up_x >= 0 && p.up_x < p.up, "gemm: bad sub-pixel output map");
+    SVDPP_CHECK_ARG(p.up == 1 || !(d->R1 || d->R2), "gemm: the sub-pixel output map takes bias/rowvec epilogues only");
     p.cstride = d->conv_stride > 1 ? d->conv_stride : 1;
     SVDPP_CHECK_ARG(p.cstride <= 2, "gemm: conv_stride=%d unsupported", d->conv_stride);
     SVDPP_CHECK_ARG(p.cstride == 1 || (d->cHin >= d->cH && d->cWin >= d->cW), "gemm: strided conv needs cHin/cWin");

@@ -92,6 +92,27 @@ class _Lin:
         self.w, self.b, self.n, self.geglu, self.impl = w, b, n, geglu, impl
 
 
+# "nearest 2x upsample, then Conv2d 3x3 pad 1" == four 2x2-tap convolutions on the low-resolution input, one per
+# output parity: for output row 2h+py the three kernel rows land on input rows {h-1, h, h} (py = 0) or {h, h, h+1}
+# (py = 1), so kernel rows that hit the same input row are summed (in fp32, rounded to fp16 once).  Same along W.
+_SUBPIX_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}   # parity -> ((input offset, kernel rows), ...)
+
+
+def subpixel_taps(py: int, px: int) -> Tuple[Tuple[int, int, int], ...]:
+    """Tap list (dw, dh, df) of the 2x2-tap convolution for output parity (py, px), K order (ih, iw, c)."""
+    return tuple((dw, dh, 0) for dh, _ in _SUBPIX_ROWS[py] for dw, _ in _SUBPIX_ROWS[px])
+
+
+def subpixel_weight(w: torch.Tensor, py: int, px: int) -> torch.Tensor:
+    """[Co, Ci, 3, 3] -> [Co, 4*Ci] for output parity (py, px); tap-major K matching ``subpixel_taps``."""
+    wf = w.float()
+    parts = []
+    for _, khs in _SUBPIX_ROWS[py]:
+        for _, kws in _SUBPIX_ROWS[px]:
+            parts.append(sum(wf[:, :, kh, kw] for kh in khs for kw in kws))
+    return torch.cat(parts, dim=1).to(w.dtype)
+
+
 def window_path_ok(W: int, C: int) -> bool:
     """Can the TMA shifted-window conv path tile rows of width W (see csrc/gemm_tc.cu)?"""
     return C % 64 == 0 and ((W >= 8 and 128 % W == 0) or W % 128 == 0)
@@ -144,6 +165,13 @@ class NativeUNet(nn.Module):
         n = w.shape[0]
         w = w.permute(0, 2, 3, 1).reshape(n, -1)              # K order (kh, kw, ci)
         return _Lin(self._keep(_pad_cols(_pad_rows(w))), self._keep(_pad_rows(self._g(prefix + ".bias"))), n)
+
+    def _conv_up(self, prefix: str):
+        """Upsampler conv as four parity convolutions: [[_Lin for px in 0, 1] for py in 0, 1]."""
+        w = self._g(prefix + ".weight")
+        b = self._keep(_pad_rows(self._g(prefix + ".bias")))
+        return [[_Lin(self._keep(_pad_cols(_pad_rows(subpixel_weight(w, py, px)))), b, w.shape[0]) for px in (0, 1)]
+                for py in (0, 1)]
 
     def _conv_t3(self, prefix: str) -> _Lin:
         w = self._g(prefix + ".weight")[:, :, :, 0, 0]        # [Co, Ci, 3]
@@ -271,6 +299,7 @@ class NativeUNet(nn.Module):
                     blk["attn"].append(self._build_transformer(f"up_blocks.{i}.attentions.{j}", rheads[i]))
             if i != len(boc) - 1:
                 blk["up"] = self._conv3x3(f"up_blocks.{i}.upsamplers.0.conv")
+                blk["up4"] = self._conv_up(f"up_blocks.{i}.upsamplers.0.conv")
             self.up.append(blk)
         self.norm_out = self._norm("conv_norm_out")
         self.conv_out = self._conv3x3("conv_out")
@@ -484,9 +513,21 @@ class NativeUNet(nn.Module):
                     x = self._transformer(x, blk["attn"][j], cvs, B, F, h, w)
             if blk["up"] is not None:
                 C = x.shape[1]
-                up = native.upsample2x(self._new(B * F * 4 * h * w, C), x, n_img=B * F, H=h, W=w, Cc=C)
-                h, w = 2 * h, 2 * w
-                x = self._conv(up, blk["up"], (B, F, h, w, C), TAPS_3X3)
+                if window_path_ok(w, C) and not os.environ.get("SVDPP_NO_SUBPIXEL"):
+                    # nearest 2x + 3x3 conv as four 2x2-tap convs on the low-resolution input (4/9 of the FLOPs, no
+                    # upsampled tensor); each GEMM scatters its rows to one output parity
+                    out = self._new(B * F * 4 * h * w, blk["up"].n)
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            lin = blk["up4"][py][px]
+                            native.gemm(out, x, lin.w, bias=lin.b, conv_dims=(B, F, h, w, C), taps=subpixel_taps(py, px),
+                                        n_store=lin.n, impl=self._impl(lin, B * F * h * w), out_up=(2, py, px))
+                    h, w = 2 * h, 2 * w
+                    x = out
+                else:
+                    up = native.upsample2x(self._new(B * F * 4 * h * w, C), x, n_img=B * F, H=h, W=w, Cc=C)
+                    h, w = 2 * h, 2 * w
+                    x = self._conv(up, blk["up"], (B, F, h, w, C), TAPS_3X3)
         a = self._gn(x, self.norm_out, n_img=B * F, HW=h * w, eps=1e-5)
         return self._conv(a, self.conv_out, (B, F, h, w, x.shape[1]), TAPS_3X3)
 

@@ -51,6 +51,7 @@ class GemmDesc(C.Structure):
         ("D", C.c_void_p), ("ldd", C.c_int64),
         ("n_store", C.c_int32),
         ("conv_stride", C.c_int32), ("cHin", C.c_int32), ("cWin", C.c_int32),
+        ("out_up", C.c_int32), ("out_up_y", C.c_int32), ("out_up_x", C.c_int32),
     ]
 
 
@@ -173,12 +174,13 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
          conv_dims: Optional[Tuple[int, int, int, int, int]] = None, taps=None,
          rowvec=None, rv_hw=1, rv_div=1, rv_mod=0, r1=None, beta1=1.0, r2=None, beta2=1.0, alpha=1.0,
          geglu=False, n_store=0, impl=0, conv_stride: int = 1,
-         conv_in_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+         conv_in_hw: Optional[Tuple[int, int]] = None, out_up: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """``out = epilogue(A @ w.T)``; see ``svdpp_gemm_desc`` in include/svdpp.h.
 
     ``a``: [M, K] (row stride may exceed K) or, with ``conv_dims=(B,F,H,W,C)``, the contiguous
     channels-last activation.  ``w``: [N, K] fp16, N a multiple of the tile width (GEGLU-interleaved if geglu).
     ``conv_stride=2`` with ``conv_in_hw=(Hin, Win)``: strided windows (conv_dims then holds the OUTPUT H, W).
+    ``out_up=(2, py, px)``: row (img, h, w) is stored at pixel (2h+py, 2w+px) of a 2H x 2W output image.
     """
     lib = load()
     d = GemmDesc()
@@ -218,6 +220,8 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
     d.alpha = alpha
     d.geglu = 1 if geglu else 0
     d.D, d.ldd = out.data_ptr(), out.stride(0)
+    if out_up is not None:
+        d.out_up, d.out_up_y, d.out_up_x = out_up
     d.n_store = n_store
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
