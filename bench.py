@@ -391,7 +391,7 @@ def main() -> None:
             d[1] += flops
             d[2] += 1
         gemm_ms = sum(agg[k][0] for k in ("conv", "linear", "geglu") if k in agg)
-        gemm_flops = fl["conv3x3"] + fl["conv_t"] + fl["conv1x1"] + fl["linear"] + fl["geglu_ff"]
+        gemm_flops = fl["conv3x3"] + fl["conv_up"] + fl["conv_t"] + fl["conv1x1"] + fl["linear"] + fl["geglu_ff"]
         n_gemm = sum(agg[k][2] for k in ("conv", "linear", "geglu") if k in agg)
         peak = peaks.get("bf16_tflops_sustained")
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"

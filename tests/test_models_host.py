@@ -114,8 +114,11 @@ def test_window_path_rule_and_flops():
     fl14 = flops_per_forward(SVD_CONFIG, 1, 14, 72, 128)
     # 79.946 TFLOP at 25 frames, including work this build never runs: the dead cross-attention q
     # projections (1.439), the cross-attention out projections on every token (1.439; here a per-image
-    # vector), the k/v projections (0.108) and the embedding MLPs (0.008)
-    assert abs(fl25["total"] / 1e12 - (79.946 - 1.439 - 1.439 - 0.108 - 0.008)) < 0.05
+    # vector), the k/v projections (0.108), the embedding MLPs (0.008) and 5/9 of the three up-sampling convs
+    # (run as four 2x2-tap parity convolutions: conv_up holds the executed 4/9)
+    ref_side = fl25["total"] + fl25["conv_up"] * 5.0 / 4.0
+    assert abs(ref_side / 1e12 - (79.946 - 1.439 - 1.439 - 0.108 - 0.008)) < 0.05
+    assert abs(fl25["conv_up"] / 1e12 - 1.699) < 0.01
     assert abs(fl25["attn_spatial"] / 1e12 - 15.503) < 0.01 and abs(fl25["geglu_ff"] / 1e12 - 25.905) < 0.01
     assert abs(fl14["total"] / fl25["total"] - 14 / 25) < 2e-3
 

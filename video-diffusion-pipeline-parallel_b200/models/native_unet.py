@@ -558,14 +558,15 @@ class NativeUNet(nn.Module):
 
 
 def flops_per_forward(cfg: dict, B: int, F: int, H: int, W: int) -> Dict[str, float]:
-    """Algorithmic FLOPs (2*M*N*K; attention 4*S^2*C per sequence) of what NativeUNet executes.
-    Unlike SURVEY.md section 8d this EXCLUDES the dead cross-attention q/k projections (1.8 %), which
-    this implementation does not run."""
+    """FLOPs (2*M*N*K; attention 4*S^2*C per sequence) of what NativeUNet EXECUTES.  Unlike the reference-side
+    count of SURVEY.md section 8d this excludes the dead cross-attention q/k projections (1.8 %) and counts the three
+    up-sampling convs at 4 instead of 9 taps (``conv_up``: they run as 2x2-tap parity convolutions), so throughput
+    figures derived from it are not inflated by work that is not done."""
     boc = tuple(cfg["block_out_channels"])
     attn = tuple(cfg["down_attn"])
     L = cfg["layers_per_block"]
-    out: Dict[str, float] = dict(conv3x3=0.0, conv_t=0.0, conv1x1=0.0, linear=0.0, geglu_ff=0.0, attn_spatial=0.0,
-                                 attn_temporal=0.0)
+    out: Dict[str, float] = dict(conv3x3=0.0, conv_up=0.0, conv_t=0.0, conv1x1=0.0, linear=0.0, geglu_ff=0.0,
+                                 attn_spatial=0.0, attn_temporal=0.0)
 
     def res(cin, cout, h, w):
         M = B * F * h * w
@@ -610,7 +611,7 @@ def flops_per_forward(cfg: dict, B: int, F: int, H: int, W: int) -> Dict[str, fl
                 tr(c, h, w)
         if i != len(boc) - 1:
             h, w = 2 * h, 2 * w
-            out["conv3x3"] += 2.0 * B * F * h * w * c * 9 * c
+            out["conv_up"] += 2.0 * B * F * h * w * c * 4 * c      # four parity convs of 2x2 taps on the h/2 x w/2 input
     out["conv3x3"] += 2.0 * B * F * h * w * cfg["out_channels"] * 9 * c
     out["total"] = sum(out.values())
     return out
