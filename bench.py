@@ -64,6 +64,11 @@ def cpu_oracle_sample(frames: int, H: int, W: int, total_steps: int, repeats: in
     import torch
     from oracle.svd_step import OracleStep, dummy_conditioning
     from oracle.unet_torch import UNetSpatioTemporalConditionModel
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 for N > 1, which would time a single-thread baseline
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     with torch.device("meta"):
         unet = UNetSpatioTemporalConditionModel()
     unet = unet.to_empty(device="cpu")
@@ -135,6 +140,10 @@ def cpu_dummy_simulator(total_steps: int = 25):
     fp32, `total_steps` steps on the host cores in one process (torch CPU kernels, as the reference runs it)."""
     import torch
     from vdpp_b200.models import DummyUNet
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(1234)
     model = DummyUNet(channels=4).eval()
     torch.manual_seed(42)
