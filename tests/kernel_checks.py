@@ -33,6 +33,27 @@ def _cmp(got: torch.Tensor, ref: torch.Tensor, rel=2e-3, floor=1e-3):
     return dict(max_err=err, tol=tol, cos=cos, ref_absmax=ref.abs().max().item(), ok=bool(finite and err <= tol))
 
 
+class _Guarded:
+    """Output buffer with canary rows before and after it: a kernel that writes outside its output (a bad scatter
+    map, an unclipped TMA store, a tail tile) trips ``intact()``.  compute-sanitizer is closed on this pool."""
+    PAD, CANARY = 64, 12345.0
+
+    def __init__(self, rows: int, cols: int, dtype=torch.float16):
+        self.buf = torch.full((rows + 2 * self.PAD, cols), self.CANARY, device=DEV, dtype=dtype)
+        self.out = self.buf[self.PAD:self.PAD + rows]
+        self.out.fill_(float("nan"))
+
+    def intact(self) -> bool:
+        torch.cuda.synchronize()
+        return bool((self.buf[:self.PAD] == self.CANARY).all() and (self.buf[-self.PAD:] == self.CANARY).all())
+
+
+def _with_guard(res: dict, g: "_Guarded") -> dict:
+    res["guard_intact"] = g.intact()
+    res["ok"] = bool(res["ok"] and res["guard_intact"])
+    return res
+
+
 def _bn(impl):
     return {3: 256, 5: 256, 4: 128, 6: 320}.get(impl, native.GEMM_BN)
 
@@ -52,7 +73,8 @@ def gemm_linear(M=300, N=320, K=320, impl=0, epilogue="full", split=False):
     a = _rand(M, K, seed=1)
     w = _rand(N, K, scale=K ** -0.5, seed=2)
     bias = _rand(N, seed=3)
-    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(M, N)
+    out = guard.out
     kw = dict(bias=_pad_n(bias, _bn(impl)))
     ref = a.float() @ w.float().t() + bias.float()
     if epilogue == "full":
@@ -69,7 +91,7 @@ def gemm_linear(M=300, N=320, K=320, impl=0, epilogue="full", split=False):
     else:
         native.gemm(out, a, _pad_n(w, _bn(impl)), n_store=N, impl=impl, **kw)
     torch.cuda.synchronize()
-    return _cmp(out, ref)
+    return _with_guard(_cmp(out, ref), guard)
 
 
 def gemm_geglu(M=260, C=128, impl=0):
@@ -107,12 +129,13 @@ def conv3x3_stride2(B=1, Fr=2, H=12, W=64, C=64, Cout=96, impl=0):
     b = _rand(Cout, seed=3)
     Ho, Wo = (H + 1) // 2, (W + 1) // 2
     wk = _pad_n(w.permute(0, 2, 3, 1).reshape(Cout, -1), _bn(impl))
-    out = torch.full((B * Fr * Ho * Wo, Cout), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(B * Fr * Ho * Wo, Cout)
+    out = guard.out
     native.gemm(out, x.reshape(-1, C), wk, bias=_pad_n(b, _bn(impl)), conv_dims=(B, Fr, Ho, Wo, C), taps=native.TAPS_3X3,
                 n_store=Cout, impl=impl, conv_stride=2, conv_in_hw=(H, W))
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=2, padding=1).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
-    return _cmp(out, ref.reshape(-1, Cout))
+    return _with_guard(_cmp(out, ref.reshape(-1, Cout)), guard)
 
 
 def conv_up2x(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
@@ -120,7 +143,8 @@ def conv_up2x(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
     x = _rand(B * Fr, H, W, C, seed=1)
     w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
     b = _rand(Cout, seed=3)
-    out = torch.full((B * Fr * 4 * H * W, Cout), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(B * Fr * 4 * H * W, Cout)
+    out = guard.out
     for py in (0, 1):
         for px in (0, 1):
             wk = _pad_n(subpixel_weight(w, py, px), _bn(impl))
@@ -129,7 +153,7 @@ def conv_up2x(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
     up = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
     ref = F.conv2d(up, w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
-    return _cmp(out, ref.reshape(-1, Cout))
+    return _with_guard(_cmp(out, ref.reshape(-1, Cout)), guard)
 
 
 def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
@@ -157,25 +181,27 @@ def attn_spatial(n_img=2, S=320, heads=2, impl=0, growing=False):
         qkv[:, :C] *= 2.0
         qkv[:, C:2 * C] *= ramp
         qkv = qkv.half()
-    out = torch.full((n_img * S, C), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(n_img * S, C)
+    out = guard.out
     native.attn_spatial(out, qkv, n_img=n_img, S=S, heads=heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125,
                         impl=impl)
     q, k, v = [t.reshape(n_img, S, heads, 64).transpose(1, 2).float() for t in qkv.split(C, dim=1)]
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_img * S, C)
     torch.cuda.synchronize()
-    return _cmp(out, ref, rel=4e-3)
+    return _with_guard(_cmp(out, ref, rel=4e-3), guard)
 
 
 def attn_temporal(B=2, Fr=5, HW=24, heads=2):
     C = heads * 64
     qkv = _rand(B * Fr * HW, 3 * C, seed=1)
-    out = torch.full((B * Fr * HW, C), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(B * Fr * HW, C)
+    out = guard.out
     native.attn_temporal(out, qkv, B=B, F=Fr, HW=HW, heads=heads, q_off=0, k_off=C, v_off=2 * C, scale=0.125)
     t = qkv.reshape(B, Fr, HW, 3, heads, 64).permute(3, 0, 2, 4, 1, 5).float()   # [3, B, HW, heads, F, 64]
     ref = F.scaled_dot_product_attention(t[0], t[1], t[2])                       # [B, HW, heads, F, 64]
     ref = ref.permute(0, 3, 1, 2, 4).reshape(B * Fr * HW, C)
     torch.cuda.synchronize()
-    return _cmp(out, ref, rel=4e-3)
+    return _with_guard(_cmp(out, ref, rel=4e-3), guard)
 
 
 # ------------------------------------------------------------------------------------------ norms
@@ -184,7 +210,8 @@ def groupnorm(n_img=4, HW=100, C1=64, C2=0, fps=1, silu=True, eps=1e-5):
     x2 = _rand(n_img * HW, C2, seed=2) if C2 else None
     C = C1 + C2
     g, b = _rand(C, seed=3), _rand(C, seed=4)
-    out = torch.full((n_img * HW, C), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(n_img * HW, C)
+    out = guard.out
     ws = torch.zeros(native.groupnorm_workspace_bytes(n_img, HW) // 4 + 1, dtype=torch.float32, device=DEV)
     for _ in range(2):   # twice through the same workspace: the arrival counters must come back to zero
         out.fill_(float("nan"))
@@ -197,7 +224,7 @@ def groupnorm(n_img=4, HW=100, C1=64, C2=0, fps=1, silu=True, eps=1e-5):
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 1).reshape(n_img * HW, C)
     torch.cuda.synchronize()
-    return _cmp(out, ref)
+    return _with_guard(_cmp(out, ref), guard)
 
 
 def layernorm(M=70, C=320, add=True):
