@@ -100,13 +100,14 @@ def gemm_geglu(M=260, C=128, impl=0):
     w = _rand(2 * inner, C, scale=C ** -0.5, seed=2)
     b = _rand(2 * inner, scale=0.1, seed=3)
     wi, bi, n = interleave_geglu(w, b, half=128 if impl == 3 else 80)
-    out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.float16)
+    guard = _Guarded(M, inner)
+    out = guard.out
     native.gemm(out, a, wi, bias=bi, geglu=True, n_store=inner, impl=impl)
     y = (a.float() @ w.float().t() + b.float()).half()
     val, gate = y.chunk(2, dim=-1)
     ref = val * F.gelu(gate)
     torch.cuda.synchronize()
-    return _cmp(out, ref, rel=4e-3)
+    return _with_guard(_cmp(out, ref, rel=4e-3), guard)
 
 
 def conv3x3(B=1, Fr=2, H=6, W=32, C=64, Cout=96, impl=0):
@@ -473,6 +474,68 @@ ALL_CHECKS = {
 }
 
 
+def _tuned(fn, **switches):
+    """Run a check with kernel tuning switches (svdpp_set_tuning) set, then restore them."""
+    def run():
+        old = {k: native.set_tuning(k, v) for k, v in switches.items()}
+        try:
+            return fn()
+        finally:
+            torch.cuda.synchronize()
+            for k, v in old.items():
+                native.set_tuning(k, v)
+    return run
+
+
+def pdl_chain(n=6):
+    """A chain of dependent launches (GEMM -> LayerNorm -> GEMM -> GroupNorm -> ...) must give bit-identical
+    results with and without programmatic dependent launch: every kernel waits for its predecessor's writes."""
+    M, C = 2304, 320
+    x0 = _rand(M, C, seed=11)
+    w = _pad_n(_rand(C, C, scale=C ** -0.5, seed=12))
+    bias = _rand(C, seed=13)
+    gam, bet = _rand(C, seed=14), _rand(C, seed=15)
+    ws = torch.zeros((native.groupnorm_workspace_bytes(4, M // 4) + 3) // 4, dtype=torch.float32, device=DEV)
+
+    def run():
+        x = x0
+        for i in range(n):
+            y = torch.empty_like(x)
+            native.gemm(y, x, w, bias=bias, r1=x, beta1=0.5, alpha=0.5, n_store=C, impl=(0, 2, 6)[i % 3])
+            z = torch.empty_like(x)
+            native.layernorm(z, y, gam, bet)
+            x = torch.empty_like(x)
+            native.groupnorm_silu(x, z, gam, bet, n_img=4, HW=M // 4, eps=1e-5, silu=True, workspace=ws)
+        torch.cuda.synchronize()
+        return x
+
+    old = native.set_tuning("pdl", 0)
+    try:
+        a = run()
+        native.set_tuning("pdl", 1)
+        b = run()
+        c = run()
+    finally:
+        native.set_tuning("pdl", old)
+    same = bool(torch.equal(a, b) and torch.equal(b, c))
+    return dict(max_err=(a.float() - b.float()).abs().max().item(), tol=0.0, ok=bool(same and torch.isfinite(a).all()))
+
+
+_LEGACY = ("tc_gemm_plain", "tc_gemm_linear", "tc_gemm_big", "tc_gemm_split", "tc_conv3x3_w32", "tc_conv_temporal",
+           "pair_gemm_linear", "pair_gemm_big", "pair256_gemm_linear", "pair256_gemm_big", "pair256_gemm_geglu_320",
+           "pair256_gemm_nstore_partial", "pair256_gemm_nstore_partial_bias", "bn128_gemm_linear", "pair320_gemm_linear",
+           "pair320_gemm_big", "pair320_conv3x3_w32", "pair256_conv_temporal")
+for _n in _LEGACY:                       # the per-thread copy-out path (tma_store = 0) stays covered
+    ALL_CHECKS["copyout_" + _n] = _tuned(ALL_CHECKS[_n], tma_store=0)
+for _n in ("tc_gemm_linear", "pair256_gemm_big", "pair320_gemm_big", "pair256_gemm_geglu_320", "tc2_attn_spatial_2304",
+           "tc_attn_spatial_tail", "attn_temporal_25_many", "groupnorm_cat_1920", "layernorm_640", "euler_cfg"):
+    ALL_CHECKS["pdl_" + _n] = _tuned(ALL_CHECKS[_n], pdl=1)
+ALL_CHECKS["pdl_chain"] = pdl_chain
+ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
+ALL_CHECKS["pair256_gemm_mtail_odd"] = lambda: gemm_linear(M=385, N=512, K=128, impl=3)   # odd tile count: one CTA of the last pair idles
+ALL_CHECKS["pair320_gemm_mtail_odd"] = lambda: gemm_linear(M=385, N=640, K=128, impl=6)
+
+
 # ------------------------------------------------------------------------------------------ whole UNet
 def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=None, seed=0):
     from oracle.unet_torch import UNetSpatioTemporalConditionModel, tiny_config
@@ -550,3 +613,6 @@ UNET_CHECKS = {
     "svd_steps_tc_cfg": lambda: svd_steps(cfg_scale=3.0),
     "svd_steps_tc_graph": lambda: svd_steps(graph=True),
 }
+UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
+UNET_CHECKS["unet_tiny_pair256_pdl"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], pdl=1)
+UNET_CHECKS["svd_steps_tc_graph_pdl"] = _tuned(UNET_CHECKS["svd_steps_tc_graph"], pdl=1)

@@ -1,0 +1,172 @@
+"""A/B of the kernel tuning switches (svdpp_set_tuning) on the full-size SVD-XT UNet step, inside ONE process:
+eager steps for every (tma_store, pdl) setting, interleaved over several rounds so that clock drift under the
+power cap hits all settings alike; final latents of all settings must be bit-identical (the switches change how a
+tile is stored / when a kernel is scheduled, never the arithmetic).  Then a per-shape GEMM table for tma_store
+0 vs 1 on the shapes of the network.  Writes gpurun_out/ab_tuning.json.
+    python tools/ab_tuning.py [--frames 25] [--rounds 3] [--steps 4] [--graph]
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import vdpp_b200  # noqa: E402,F401
+from vdpp_b200 import native  # noqa: E402
+from vdpp_b200.models import StableVideoUNet  # noqa: E402
+
+
+def time_steps(model, x, n):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    y = x
+    for s in range(n):
+        y = model(y, s)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, y.clone()
+
+
+def gemm_table(dev):
+    """(M, N, K, impl, residual) of the layers the copy-out loop hurt most, and a few long-K controls."""
+    shapes = [
+        (230400, 320, 320, 0, True), (230400, 320, 320, 0, False), (230400, 1024, 320, 3, False),
+        (230400, 320, 1280, 6, True), (57600, 640, 640, 0, True), (57600, 2048, 640, 3, False),
+        (57600, 640, 2560, 6, True), (14400, 1280, 1280, 3, True), (14400, 1280, 5120, 3, True),
+        (14400, 3840, 1280, 3, False), (230400, 320, 2880, 6, False), (3600, 1280, 1280, 3, True),
+    ]
+    rows = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for M, N, K, impl, res in shapes:
+        a = (torch.randn(M, K, device=dev) * 0.5).half()
+        w = (torch.randn(N, K, device=dev) * K ** -0.5).half()
+        bias = torch.randn(N, device=dev).half()
+        r1 = torch.randn(M, N, device=dev).half() if res else None
+        outs, ms = {}, {}
+        for tst in (0, 1, 0, 1):
+            native.set_tuning("tma_store", tst)
+            out = torch.empty(M, N, device=dev, dtype=torch.float16)
+            for _ in range(2):
+                native.gemm(out, a, w, bias=bias, r1=r1, n_store=N, impl=impl)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                native.gemm(out, a, w, bias=bias, r1=r1, n_store=N, impl=impl)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 10
+            ms[tst] = min(ms.get(tst, 1e9), t)
+            outs[tst] = out
+        rows.append(dict(M=M, N=N, K=K, impl=impl, residual=res, copyout_us=round(ms[0] * 1e3, 1),
+                         tma_store_us=round(ms[1] * 1e3, 1), speedup=round(ms[0] / ms[1], 3),
+                         tflops_tma=round(2.0 * M * N * K / ms[1] / 1e9, 1), identical=bool(torch.equal(outs[0], outs[1]))))
+        print(rows[-1], flush=True)
+        del a, w, r1, outs
+    native.set_tuning("tma_store", 1)
+    return rows
+
+
+def geglu_table(dev):
+    from vdpp_b200.models.native_unet import interleave_geglu
+    rows = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for M, C in ((230400, 320), (57600, 640), (14400, 1280)):
+        inner = 4 * C
+        a = (torch.randn(M, C, device=dev) * 0.5).half()
+        w = (torch.randn(2 * inner, C, device=dev) * C ** -0.5).half()
+        b = (torch.randn(2 * inner, device=dev) * 0.1).half()
+        wi, bi, n = interleave_geglu(w, b, half=128)
+        ms, outs = {}, {}
+        for tst in (0, 1, 0, 1):
+            native.set_tuning("tma_store", tst)
+            out = torch.empty(M, inner, device=dev, dtype=torch.float16)
+            for _ in range(2):
+                native.gemm(out, a, wi, bias=bi, geglu=True, n_store=inner, impl=3)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                native.gemm(out, a, wi, bias=bi, geglu=True, n_store=inner, impl=3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms[tst] = min(ms.get(tst, 1e9), e0.elapsed_time(e1) / 10)
+            outs[tst] = out
+        rows.append(dict(kind="geglu", M=M, C=C, copyout_us=round(ms[0] * 1e3, 1), tma_store_us=round(ms[1] * 1e3, 1),
+                         speedup=round(ms[0] / ms[1], 3), tflops_tma=round(2.0 * M * 2 * inner * C / ms[1] / 1e9, 1),
+                         identical=bool(torch.equal(outs[0], outs[1]))))
+        print(rows[-1], flush=True)
+    native.set_tuning("tma_store", 1)
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=25)
+    ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays of a step per setting")
+    ap.add_argument("--no-tables", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    F_, H, W = a.frames, 72, 128
+    model = StableVideoUNet.from_pretrained("random-init:0", device=dev)
+    torch.manual_seed(1)
+    model.set_dummy_conditioning(1, F_, H, W, dev)
+    x = torch.randn(1, 4, F_, H, W, device=dev).half() * model.init_noise_sigma
+    settings = list(itertools.product((0, 1), (0, 1)))      # (tma_store, pdl)
+    default = (native.get_tuning("tma_store"), native.get_tuning("pdl"))
+    res = {"frames": F_, "default": default, "eager_ms": {}, "identical": True}
+    ref = None
+    for tst, pdl in settings:                               # warm-up + bit-equality
+        native.set_tuning("tma_store", tst)
+        native.set_tuning("pdl", pdl)
+        _, y = time_steps(model, x, 2)
+        if ref is None:
+            ref = y
+        same = bool(torch.equal(ref, y))
+        res["identical"] = res["identical"] and same
+        print(f"tma_store={tst} pdl={pdl}: finite={bool(torch.isfinite(y).all())} identical_to_first={same}", flush=True)
+    for r in range(a.rounds):
+        for tst, pdl in settings:
+            native.set_tuning("tma_store", tst)
+            native.set_tuning("pdl", pdl)
+            ms, _ = time_steps(model, x, a.steps)
+            res["eager_ms"].setdefault(f"tma{tst}_pdl{pdl}", []).append(round(ms, 3))
+            print(f"round {r} tma_store={tst} pdl={pdl}: {ms:.3f} ms/step", flush=True)
+    if a.graph:
+        res["graph_ms"] = {}
+        model.use_cuda_graph = True
+        for tst, pdl in settings:
+            native.set_tuning("tma_store", tst)
+            native.set_tuning("pdl", pdl)
+            model._graphs.clear()                           # re-capture under this setting
+            try:
+                time_steps(model, x, a.steps)               # warm-up + capture of steps 0..steps-1
+                ms, y = time_steps(model, x, a.steps)
+                same = bool(torch.equal(ref2, y)) if "ref2" in locals() else True
+                ref2 = y if "ref2" not in locals() else ref2
+                res["graph_ms"][f"tma{tst}_pdl{pdl}"] = round(ms, 3)
+                res["identical"] = res["identical"] and same
+                print(f"graph tma_store={tst} pdl={pdl}: {ms:.3f} ms/step identical={same}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                res["graph_ms"][f"tma{tst}_pdl{pdl}"] = f"failed: {e}"
+                print("graph failed", tst, pdl, e, flush=True)
+        model._graphs.clear()
+        model.use_cuda_graph = False
+    native.set_tuning("tma_store", default[0])
+    native.set_tuning("pdl", default[1])
+    if not a.no_tables:
+        res["gemm"] = gemm_table(dev)
+        res["geglu"] = geglu_table(dev)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ab_tuning.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k not in ("gemm", "geglu")}))
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,8 @@ attn_temporal_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_
     fence_mbar_init();
   }
   __syncwarp();
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
 
   const long long stride = static_cast<long long>(gridDim.x) * TA_WARPS;
   long long unit = static_cast<long long>(blockIdx.x) * TA_WARPS + warp;
@@ -253,7 +255,7 @@ static int launch_ta(const CUtensorMap& tmIn, const CUtensorMap& tmOut, const TA
   }
   long long blocks = (p.units + WARPS - 1) / WARPS;
   if (blocks > static_cast<long long>(num_sms()) * CTAS_PER_SM) blocks = static_cast<long long>(num_sms()) * CTAS_PER_SM;
-  kern<<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(tmIn, tmOut, p);
+  SVDPP_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(WARPS * 32), smem, stream, 1, tmIn, tmOut, p));
   return check_launch("attn_temporal_mma_kernel");
 }
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace svdpp {
 
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(512)
 gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int pix,
                   int n_chunks, int n_items, int ipc, int n_slots, float2* partial, double2* imgsum, unsigned* counters,
                   int frames_per_stat, float count, float eps, float2* __restrict__ stats) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t gn_smem[];
   __shared__ int s_last;
   __shared__ __align__(8) uint64_t s_bar[8];
@@ -267,6 +270,8 @@ __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, const float2* __restrict__ stats,
                 __half* __restrict__ out, int HW, int pix, int frames_per_stat, int silu) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const int C = C1 + C2;
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
@@ -318,6 +323,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
                  int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                  __half* __restrict__ out, long long ldo, int M, int C, float eps) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (m >= M) return;
@@ -381,6 +388,8 @@ __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
                       int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                       __half* __restrict__ out, long long ldo, int M, float eps) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   constexpr int C = 40 * LPR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -441,6 +450,8 @@ linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ x_a
                     const __half* __restrict__ W, long long ldw,
                     const __half* __restrict__ bias, __half* __restrict__ y, long long ldy, int R, int N, int K,
                     int act_in, int act_out) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 4 + warp;
   if (n >= N) return;
@@ -503,6 +514,8 @@ static_assert(sizeof(SmallGroup) == sizeof(svdpp_small_group), "ABI struct misma
 __global__ void __launch_bounds__(128)
 linear_small_grouped_kernel(const __half* __restrict__ x, long long ldx, const SmallGroup* __restrict__ groups,
                             __half* __restrict__ y, long long ldy, int R) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const SmallGroup gr = groups[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 4 + warp;
@@ -543,6 +556,8 @@ linear_small_grouped_kernel(const __half* __restrict__ x, long long ldx, const S
 // ------------------------------------------------------------------------------------ sinusoid
 __global__ void sinusoid_kernel(const void* __restrict__ src, int src_kind, int src_mod, int n_vals, int dim,
                                 __half* __restrict__ out) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const int half_dim = dim >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_vals * half_dim) return;
@@ -582,6 +597,8 @@ struct Taps {
 
 __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long ldo, int F, int H,
                               int W, int C, int Ho, int Wo, int stride, int ntaps, Taps taps, long long n_vec) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const int vpr = static_cast<int>(ldo >> 3);
   const int K = ntaps * C;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n_vec;
@@ -609,6 +626,8 @@ __global__ void pack_unet_input_kernel(const __half* __restrict__ s0, long long 
                                        int C0, float in_div, const __half* __restrict__ s1, long long s1b,
                                        long long s1f, long long s1c, int C1, __half* __restrict__ out,
                                        int out_bfchw, int B, int F, int HW) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const long long total = static_cast<long long>(B) * F * HW;
   const int C = C0 + C1;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -629,6 +648,8 @@ __global__ void pack_unet_input_kernel(const __half* __restrict__ s0, long long 
 
 __global__ void nhwc_to_bfchw_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long total, int C,
                                      int HW) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int p = static_cast<int>(idx % HW);
@@ -642,6 +663,8 @@ __global__ void euler_vpred_kernel(const __half* __restrict__ latent, const __ha
                                    const __half* __restrict__ vc, const __half* __restrict__ gs, int v_nhwc,
                                    float c_v, float c_x, float sigma, float dt, __half* __restrict__ out, int B,
                                    int C, int F, int HW) {
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
   const long long total = static_cast<long long>(B) * F * HW;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -806,7 +829,7 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   int stat_blocks = 2 * num_sms();  // persistent: two blocks per SM, each prefetching its next chunk
   if (stat_blocks > n_items) stat_blocks = n_items;
   const int ipc = (n_items + stat_blocks - 1) / stat_blocks;  // contiguous items per block
-  gn_partial_kernel<<<stat_blocks, block, smem_bytes, stream>>>(static_cast<const __half*>(x1), C1,
+  launch_kernel(gn_partial_kernel, dim3(stat_blocks), dim3(block), smem_bytes, stream, 1, static_cast<const __half*>(x1), C1,
                                                                 static_cast<const __half*>(x2), C2, HW, pix, n_chunks,
                                                                 n_items, ipc, n_slots, partial, imgsum, counters,
                                                                 frames_per_stat, count, eps, stats);
@@ -820,7 +843,7 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   int apix = pix;
   while (apix < apply_max && static_cast<long long>(n_img) * ((HW + 2 * apix - 1) / (2 * apix)) >= 4LL * num_sms()) apix <<= 1;
   dim3 grid_apply((HW + apix - 1) / apix, n_img);
-  gn_apply_kernel<<<grid_apply, block, 0, stream>>>(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
+  launch_kernel(gn_apply_kernel, dim3(grid_apply), dim3(block), 0, stream, 1, static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                               stats, static_cast<__half*>(out), HW, apix, frames_per_stat, apply_silu);
   return check_launch("gn_apply_kernel");
@@ -841,13 +864,13 @@ extern "C" int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, i
   __half* oh = static_cast<__half*>(out);
   const int hw = add_hw > 0 ? add_hw : 1, md = add_mod > 0 ? add_mod : 1;
   if (C == 320)
-    layernorm_rows_kernel<8><<<(M + 31) / 32, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<8>, dim3((M + 31) / 32), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
   else if (C == 640)
-    layernorm_rows_kernel<16><<<(M + 15) / 16, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<16>, dim3((M + 15) / 16), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
   else if (C == 1280)
-    layernorm_rows_kernel<32><<<(M + 7) / 8, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<32>, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
   else
-    layernorm_kernel<<<(M + 7) / 8, 256, 0, stream>>>(xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, C, eps);
+    launch_kernel(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, C, eps);
   return check_launch("layernorm_kernel");
 }
 
@@ -858,7 +881,7 @@ extern "C" int svdpp_linear_small(const void* x, const void* x_add, int64_t ldx,
   SVDPP_CHECK_ARG(x && W && y, "linear_small: null pointer");
   SVDPP_CHECK_ARG(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "linear_small: K and pitches must be multiples of 8");
   SVDPP_CHECK_ARG(R >= 1 && N >= 1, "linear_small: bad shape");
-  linear_small_kernel<<<(N + 3) / 4, 128, 0, stream>>>(static_cast<const __half*>(x),
+  launch_kernel(linear_small_kernel, dim3((N + 3) / 4), dim3(128), 0, stream, 1, static_cast<const __half*>(x),
                                                        static_cast<const __half*>(x_add), ldx,
                                                        static_cast<const __half*>(W), ldw,
                                                        static_cast<const __half*>(bias), static_cast<__half*>(y), ldy,
@@ -874,7 +897,7 @@ extern "C" int svdpp_linear_small_grouped(const void* x, int64_t ldx, const svdp
   SVDPP_CHECK_ARG(n_groups >= 1 && n_groups <= 65535 && max_n >= 1 && R >= 1, "linear_small_grouped: bad shape");
   SVDPP_CHECK_ARG(ldx % 8 == 0, "linear_small_grouped: ldx must be a multiple of 8");
   dim3 grid((max_n + 3) / 4, n_groups);
-  linear_small_grouped_kernel<<<grid, 128, 0, stream>>>(static_cast<const __half*>(x), ldx,
+  launch_kernel(linear_small_grouped_kernel, dim3(grid), dim3(128), 0, stream, 1, static_cast<const __half*>(x), ldx,
                                                         reinterpret_cast<const SmallGroup*>(groups_dev),
                                                         static_cast<__half*>(y), ldy, R);
   return check_launch("linear_small_grouped_kernel");
@@ -886,7 +909,7 @@ extern "C" int svdpp_sinusoid_embed(const void* src, int32_t src_kind, int32_t s
   SVDPP_CHECK_ARG(out && dim % 2 == 0 && n_vals > 0, "sinusoid: bad arguments");
   SVDPP_CHECK_ARG(src_kind == 2 ? src_mod > 0 : src != nullptr, "sinusoid: bad source");
   const int total = n_vals * (dim / 2);
-  sinusoid_kernel<<<(total + 127) / 128, 128, 0, stream>>>(src, src_kind, src_mod, n_vals, dim,
+  launch_kernel(sinusoid_kernel, dim3((total + 127) / 128), dim3(128), 0, stream, 1, src, src_kind, src_mod, n_vals, dim,
                                                            static_cast<__half*>(out));
   return check_launch("sinusoid_kernel");
 }
@@ -912,7 +935,7 @@ extern "C" int svdpp_im2col_nhwc(const void* x, void* out, int64_t ldo, int32_t 
   for (int i = 0; i < ntaps; ++i)
     for (int j = 0; j < 4; ++j) t.t[i][j] = taps[i * 4 + j];
   const long long n_vec = static_cast<long long>(B) * F * Ho * Wo * (ldo / 8);
-  im2col_kernel<<<grid_for(n_vec, 256), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out),
+  launch_kernel(im2col_kernel, dim3(grid_for(n_vec, 256)), dim3(256), 0, stream, 1, static_cast<const __half*>(x), static_cast<__half*>(out),
                                                           ldo, F, H, W, C, Ho, Wo, stride, ntaps, t, n_vec);
   return check_launch("im2col_kernel");
 }
@@ -925,7 +948,7 @@ extern "C" int svdpp_pack_unet_input(const void* src0, int64_t s0_b, int64_t s0_
   if (src1 == nullptr) C1 = 0;
   SVDPP_CHECK_ARG(src0 && out && C0 > 0, "pack_unet_input: bad arguments");
   const long long total = static_cast<long long>(B) * F * H * W;
-  pack_unet_input_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+  launch_kernel(pack_unet_input_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 1, 
       static_cast<const __half*>(src0), s0_b, s0_f, s0_c, C0, in_div, static_cast<const __half*>(src1), s1_b, s1_f,
       s1_c, C1, static_cast<__half*>(out), out_bfchw, B, F, H * W);
   return check_launch("pack_unet_input_kernel");
@@ -936,7 +959,7 @@ extern "C" int svdpp_nhwc_to_bfchw(const void* x, void* out, int32_t B, int32_t 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SVDPP_CHECK_ARG(x && out, "nhwc_to_bfchw: null pointer");
   const long long total = static_cast<long long>(B) * F * H * W;
-  nhwc_to_bfchw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __half*>(x),
+  launch_kernel(nhwc_to_bfchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 1, static_cast<const __half*>(x),
                                                                  static_cast<__half*>(out), total, C, H * W);
   return check_launch("nhwc_to_bfchw_kernel");
 }
@@ -948,7 +971,7 @@ extern "C" int svdpp_euler_vpred_step(const void* latent, const void* v_a, const
   SVDPP_CHECK_ARG(latent && v_a && out, "euler: null pointer");
   SVDPP_CHECK_ARG(v_cond == nullptr || gs != nullptr, "euler: guidance needs gs");
   const long long total = static_cast<long long>(B) * F * H * W;
-  euler_vpred_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+  launch_kernel(euler_vpred_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 1, 
       static_cast<const __half*>(latent), static_cast<const __half*>(v_a), static_cast<const __half*>(v_cond),
       static_cast<const __half*>(gs), v_nhwc, c_v, c_x, sigma, dt, static_cast<__half*>(out), B, C, F, H * W);
   return check_launch("euler_vpred_kernel");

@@ -4,6 +4,8 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
+#include <string.h>
 
 namespace svdpp {
 
@@ -29,6 +31,18 @@ int num_sms() {
   return cached;
 }
 
+Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning v;
+    const char* e = getenv("SVDPP_NO_TMA_STORE");
+    v.tma_store = (e != nullptr && e[0] != '0') ? 0 : 1;
+    e = getenv("SVDPP_PDL");
+    v.pdl = (e != nullptr && e[0] != '0') ? 1 : 0;
+    return v;
+  }();
+  return t;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -48,7 +62,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                    int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -65,7 +80,8 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank=%d dims=[%llu,%llu,..] stride0=%llu box=[%u,%u,..] base=%p",
@@ -83,6 +99,28 @@ extern "C" {
 int svdpp_abi_version(void) { return SVDPP_ABI_VERSION; }
 
 const char* svdpp_last_error(void) { return svdpp::g_err; }
+
+static int* tuning_slot(const char* key) {
+  if (key == nullptr) return nullptr;
+  if (strcmp(key, "tma_store") == 0) return &svdpp::tuning().tma_store;
+  if (strcmp(key, "pdl") == 0) return &svdpp::tuning().pdl;
+  return nullptr;
+}
+
+int svdpp_set_tuning(const char* key, int value) {
+  int* s = tuning_slot(key);
+  if (s == nullptr) {
+    svdpp::set_error("unknown tuning key '%s'", key ? key : "(null)");
+    return -1;
+  }
+  *s = value;
+  return 0;
+}
+
+int svdpp_get_tuning(const char* key) {
+  int* s = tuning_slot(key);
+  return s ? *s : -1;
+}
 
 int svdpp_device_info(int* sm_major, int* sm_minor, int* n_sms) {
   int dev = 0;

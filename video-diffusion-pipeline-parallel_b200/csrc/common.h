@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 #include "../../include/svdpp.h"
 
@@ -40,11 +41,49 @@ inline int check_launch(const char* what) {
 
 int num_sms();
 
-// fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first;
+// Process-wide tuning switches (svdpp_set_tuning; defaults from the environment).
+struct Tuning {
+  int tma_store;  // GEMM output tiles through TMA tensor stores
+  int pdl;        // programmatic dependent launch on every kernel
+};
+Tuning& tuning();
+
+// Launch through cudaLaunchKernelEx so that the cluster shape and programmatic stream serialisation can be
+// attached.  With PDL every kernel executes griddepcontrol.wait (pdl_wait() in ptx.cuh) before its first access to
+// global memory, which orders it after the COMPLETION of the previous kernel: only prologues overlap.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (tuning().pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// fp16 tensor map, 128-byte swizzle (swizzle_bytes: 128 or 64), zero fill out of bounds. dims/box innermost first;
 // strides_bytes has rank-1 entries (dimension 0 is contiguous).
 // elem_strides (optional): traversal stride per dimension; a box of extent box[i] then loads
 // ceil(box[i] / elem_strides[i]) elements (used for the stride-2 down-sampling convolutions).
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr,
+                    int swizzle_bytes = 128);
 
 }  // namespace svdpp

@@ -144,6 +144,8 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
 
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
@@ -371,7 +373,7 @@ static int launch_a2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Attn
     SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, A2Cfg<SPLIT>::THREADS, A2_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  SVDPP_CUDA(launch_kernel(kern, grid, dim3(A2Cfg<SPLIT>::THREADS), A2_SMEM_BYTES, stream, 1, tmQ, tmKV, p));
   return check_launch("attn_spatial2_tc_kernel");
 }
 

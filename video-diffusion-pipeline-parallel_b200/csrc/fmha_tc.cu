@@ -92,6 +92,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 128;  // S buffers: columns [0,64) and [64,128); O: [128,192)
+  pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
+  pdl_wait();
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
@@ -355,6 +357,6 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
     configured = true;
   }
   dim3 grid((d->S + 127) / 128, d->heads, d->n_img);
-  attn_spatial_tc_kernel<<<grid, 192, ATT_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  SVDPP_CUDA(launch_kernel(attn_spatial_tc_kernel, grid, dim3(192), ATT_SMEM_BYTES, stream, 1, tmQ, tmKV, p));
   return check_launch("attn_spatial_tc_kernel");
 }

@@ -42,6 +42,9 @@ struct GemmParams {
   // sub-pixel output map (conv mode, up > 1): GEMM row m = pixel (img, h, w) of the cH x cW grid is stored at pixel
   // (up*h + up_y, up*w + up_x) of the (up*cH) x (up*cW) output image
   int up, up_y, up_x;
+  // 1: the output tile leaves through TMA tensor stores (tmD) from a 64-byte-swizzled staging tile instead of the
+  // per-thread smem -> global copy loop (ncu: that loop held 48 % of the epilogue warps' samples on the K = 320 layers)
+  int tma_store;
 };
 
 // Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
@@ -149,7 +152,8 @@ struct GemmCfg {
 template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 __global__ void __launch_bounds__(GemmCfg<BN, GEGLU, TWO, EW_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+               const GemmParams p) {
   using Cfg = GemmCfg<BN, GEGLU, TWO, EW_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -174,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -201,6 +206,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) may run
+  // while the previous kernel drains; nothing below starts before that kernel has completed.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -373,6 +382,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NV = Cfg::BM * VPR / ET;  // staged vectors per thread
     static_assert(Cfg::BM * VPR % ET == 0 && (SW / CW) % WPQ == 0, "epilogue work split");
     auto epi_bar = [&] { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(ET) : "memory"); };
+    // TMA-store mode: the staging tile is SW/32 boxes of [128 rows][32 columns] (8 KB each) in the 64-byte swizzle
+    // of tmD: 16-byte piece j of row r sits at r * 64 + ((j ^ ((r >> 1) & 3)) << 4), so the row-per-thread accesses
+    // of a quarter warp cover 128 contiguous bytes (no bank conflicts) and one thread per group stores the tile.
+    const bool tst = p.tma_store != 0;
+    uint8_t* sCb = reinterpret_cast<uint8_t*>(sC);
+    auto stage_vec = [&](int r, int v) -> uint4* {  // 16-byte vector v of staged row r
+      if (tst) return reinterpret_cast<uint4*>(sCb + (v >> 2) * 8192 + r * 64 + (((v & 3) ^ ((r >> 1) & 3)) << 4));
+      return reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8);
+    };
     int as = Cfg::GROUPS == 2 ? grp : 0;  // with two groups each owns one TMEM stage
     uint32_t aphase = 0;
     int it = grp;
@@ -397,7 +415,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(we * 32) << 16);
-      __half* srow = sC + row * Cfg::C_PITCH;
 #pragma unroll 1
       for (int rd = 0; rd < Cfg::ROUNDS; ++rd) {
         const int col0 = rd * SW;                       // first column of this round within the tile
@@ -427,7 +444,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const int i = et + k * ET;
-              const int r = i / VPR, v = i - r * VPR;
+              // TMA-store mode walks box by box, four threads per 64-byte row piece (matches the swizzled layout)
+              const int r = tst ? (i & 511) >> 2 : i / VPR, v = tst ? ((i >> 9) << 2) | (i & 3) : i - r * VPR;
               val[k] = make_uint4(0, 0, 0, 0);
               if (m_base + r < p.M) {
                 const __half* src = p.R1 + static_cast<long long>(m_base + r) * p.ldr1 + nout0 + v * 8;
@@ -442,14 +460,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
+            if (tst) {
+              if (et == 0) bulk_wait_group_read<0>();  // the previous round's tensor store has read the staging tile
+              epi_bar();
+            }
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const int i = et + k * ET;
-              const int r = i / VPR, v = i - r * VPR;
-              *reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8) = val[k];
+              const int r = tst ? (i & 511) >> 2 : i / VPR, v = tst ? ((i >> 9) << 2) | (i & 3) : i - r * VPR;
+              *stage_vec(r, v) = val[k];
             }
           }
         }
+        if (tst && (GEGLU || p.R1 == nullptr) && et == 0) bulk_wait_group_read<0>();  // ... staging tile is free
         epi_bar();
         if (rd == 0) {
           if constexpr (Cfg::ROT3)
@@ -516,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float b8[8];
 #pragma unroll
               for (int hlf = 0; hlf < CW / 8; ++hlf) {
-                load8(srow + c * CW + hlf * 8, b8);
+                load8(reinterpret_cast<const __half*>(stage_vec(row, (c * CW) / 8 + hlf)), b8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
               }
@@ -533,11 +556,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < CW; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(srow + c * CW);
           const uint4* o4 = reinterpret_cast<const uint4*>(o);
 #pragma unroll
-          for (int q = 0; q < CW / 8; ++q) d4[q] = o4[q];
+          for (int q = 0; q < CW / 8; ++q) *stage_vec(row, (c * CW) / 8 + q) = o4[q];
         }
+        if (tst) fence_proxy_async_smem();  // staged results -> visible to the TMA engine
         if constexpr (Cfg::ROT3) {
           tc_fence_before();
           mbar_arrive_cluster(&tempty[rot_buf], 0);  // this half's buffer is free for the tile after next... or next
@@ -549,6 +572,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(&tempty[as]);  // accumulator stage free: the next tile's MMAs may start
         }
         epi_bar();
+        if (tst) {
+          if (et == 0 && m_base < p.M) {
+#pragma unroll
+            for (int b = 0; b < SW / 32; ++b)
+              if (nout0 + b * 32 < p.n_store) tma_store_2d(&tmD, sCb + b * 8192, nout0 + b * 32, m_base);
+            bulk_commit_group();
+          }
+          continue;  // the staging tile is handed back by the wait at the top of the next round
+        }
         for (int i = et; i < Cfg::BM * VPR; i += ET) {
           const int r = i / VPR, v = i - r * VPR;
           if (m_base + r < p.M) {
@@ -574,6 +606,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         aphase ^= 1;
       }
     }
+    if (tst && et == 0) bulk_wait_group<0>();  // the staging tile must outlive the last tensor store
   }
 
   tc_fence_before();
@@ -672,7 +705,7 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
 
 template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                     const GemmParams& p, cudaStream_t stream) {
+                     const GemmParams& p_in, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, GEGLU, TWO, EW_>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, GEGLU, TWO, EW_>;
@@ -680,28 +713,32 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  GemmParams p = p_in;
+  // Output through TMA tensor stores: rows of 32 columns (64 bytes) per box, 64-byte swizzle; the tensor map's
+  // extents [n_store, M] clip the N padding and the M tail.  Not for the sub-pixel output map (rows scatter), for
+  // row pitches that are not 16-byte multiples, or for the 80-column GEGLU round of the 160-wide tile.
+  CUtensorMap tmD = tmB;
+  p.tma_store = 0;
+  if (tuning().tma_store && Cfg::SW % 32 == 0 && p.up <= 1 && (p.ldd & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
+    static_assert(Cfg::SW % 32 != 0 || (Cfg::SW / 32) * 8192 <= Cfg::C_BYTES, "swizzled staging tile fits");
+    uint64_t dims[2] = {static_cast<uint64_t>(p.n_store), static_cast<uint64_t>(p.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(p.ldd) * 2};
+    uint32_t box[2] = {32, 128};
+    if (encode_tmap_f16(&tmD, p.D, 2, dims, str, box, nullptr, 64)) return -5;
+    p.tma_store = 1;
+  }
   if constexpr (TWO) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     int clusters = num_sms() / 2;
     if (pairs < clusters) clusters = pairs;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SVDPP_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, p));
+    SVDPP_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 2, tmA, tmA2, tmB,
+                             tmD, p));
     return check_launch("gemm_tc_kernel<pair>");
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+  SVDPP_CUDA(launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmA2, tmB, tmD, p));
   return check_launch("gemm_tc_kernel");
 }
 

@@ -18,7 +18,8 @@ MAX_TAPS = 9
 GEMM_BN = 160  # N tile of the tcgen05 GEMM; weights are padded / GEGLU-interleaved to it
 
 EXPORTED_SYMBOLS = (
-    "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_gemm_f16",
+    "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_set_tuning", "svdpp_get_tuning",
+    "svdpp_gemm_f16",
     "svdpp_attn_spatial_f16", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
     "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_linear_small_grouped",
     "svdpp_sinusoid_embed",
@@ -94,6 +95,8 @@ def load():
     lib = C.CDLL(str(_LIB_PATH))
     lib.svdpp_last_error.restype = C.c_char_p
     lib.svdpp_abi_version.restype = C.c_int
+    lib.svdpp_set_tuning.argtypes = [C.c_char_p, C.c_int]
+    lib.svdpp_get_tuning.argtypes = [C.c_char_p]
     lib.svdpp_groupnorm_workspace_bytes.restype = C.c_size_t
     lib.svdpp_groupnorm_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.svdpp_gemm_f16.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_void_p]
@@ -150,6 +153,20 @@ def _req(t: torch.Tensor, dtype=torch.float16) -> None:
         raise NativeError("native kernels need CUDA tensors (there is no CPU path)")
     if t.dtype != dtype:
         raise NativeError(f"expected dtype {dtype}, got {t.dtype}")
+
+
+def set_tuning(key: str, value: int) -> int:
+    """Set a process-wide kernel tuning switch ("tma_store", "pdl"; include/svdpp.h); returns the previous value."""
+    old = get_tuning(key)
+    _check(load().svdpp_set_tuning(key.encode(), int(value)), "svdpp_set_tuning")
+    return old
+
+
+def get_tuning(key: str) -> int:
+    v = load().svdpp_get_tuning(key.encode())
+    if v < 0:
+        raise NativeError(f"unknown tuning key {key!r}")
+    return v
 
 
 def device_info() -> Tuple[int, int, int]:
