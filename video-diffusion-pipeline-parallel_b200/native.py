@@ -83,16 +83,8 @@ def library_path() -> pathlib.Path:
     return _LIB_PATH
 
 
-def load():
-    """Load libsvdpp.so (once). Raises NativeError if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not _LIB_PATH.exists():
-        raise NativeError(
-            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a). There is no CPU or library fallback for this path.")
-    lib = C.CDLL(str(_LIB_PATH))
+def _bind(lib):
+    """Declare the argument types of every entry point on a freshly dlopen-ed libsvdpp."""
     lib.svdpp_last_error.restype = C.c_char_p
     lib.svdpp_abi_version.restype = C.c_int
     lib.svdpp_set_tuning.argtypes = [C.c_char_p, C.c_int]
@@ -129,6 +121,28 @@ def load():
                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.svdpp_dummy_unet_step.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_int32] * 6 + [C.c_void_p]
+    return lib
+
+
+def use_library(path) -> None:
+    """Swap in another build of libsvdpp.so (A/B measurements of two builds inside one process: tools/ab_lib.py)."""
+    global _lib
+    lib = _bind(C.CDLL(str(path)))
+    if lib.svdpp_abi_version() != 1:
+        raise NativeError("libsvdpp.so ABI version mismatch; rebuild")
+    _lib = lib
+
+
+def load():
+    """Load libsvdpp.so (once). Raises NativeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise NativeError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or library fallback for this path.")
+    lib = _bind(C.CDLL(str(_LIB_PATH)))
     if lib.svdpp_abi_version() != 1:
         raise NativeError("libsvdpp.so ABI version mismatch; rebuild")
     _lib = lib
