@@ -33,9 +33,10 @@ const char* svdpp_last_error(void);
 /* compute capability and SM count of the current device; <0 if no usable device */
 int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
 /* Tuning switches of the kernels (process-wide; initial values come from the environment when the library is
- * loaded: SVDPP_NO_TMA_STORE=1 -> "tma_store" = 0, SVDPP_PDL=1 -> "pdl" = 1).  They change HOW a result is
+ * loaded: SVDPP_NO_TMA_STORE=1 -> "tma_store" = 0, SVDPP_NO_TMA_R1=1 -> "tma_r1" = 0, SVDPP_PDL=1 -> "pdl" = 1).  They change HOW a result is
  * produced, never the result (tests/test_gpu_kernels.py runs both settings against the oracle):
  *   "tma_store"  1: GEMM output tiles leave through TMA tensor stores; 0: per-thread copy loop
+ *   "tma_r1"     1 (with tma_store): the residual tile R1 reaches the epilogue through TMA tensor loads; 0: per-thread loads
  *   "pdl"        1: kernels are launched with programmatic stream serialisation (the prologue of kernel N+1
  *                   overlaps the tail of kernel N; every kernel waits on griddepcontrol before touching memory)
  * set returns 0, or -1 for an unknown key; get returns the value, or -1 for an unknown key.

@@ -531,9 +531,13 @@ for _n in ("tc_gemm_linear", "pair256_gemm_big", "pair320_gemm_big", "pair256_ge
            "tc_attn_spatial_tail", "attn_temporal_25_many", "groupnorm_cat_1920", "layernorm_640", "euler_cfg"):
     ALL_CHECKS["pdl_" + _n] = _tuned(ALL_CHECKS[_n], pdl=1)
 ALL_CHECKS["pdl_chain"] = pdl_chain
-ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
 ALL_CHECKS["pair256_gemm_mtail_odd"] = lambda: gemm_linear(M=385, N=512, K=128, impl=3)   # odd tile count: one CTA of the last pair idles
 ALL_CHECKS["pair320_gemm_mtail_odd"] = lambda: gemm_linear(M=385, N=640, K=128, impl=6)
+for _n in ("tc_gemm_linear", "tc_gemm_big", "tc_gemm_split", "pair_gemm_big", "pair256_gemm_linear", "pair256_gemm_big",
+           "pair256_gemm_nstore_partial", "pair320_gemm_linear", "pair320_gemm_big", "bn128_gemm_big",
+           "pair256_gemm_mtail_odd", "pair320_gemm_mtail_odd"):
+    ALL_CHECKS["r1ldg_" + _n] = _tuned(ALL_CHECKS[_n], tma_r1=0)       # residual tile through per-thread loads (TMA loads are the default)
+ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
 
 
 # ------------------------------------------------------------------------------------------ whole UNet
@@ -615,4 +619,5 @@ UNET_CHECKS = {
 }
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
 UNET_CHECKS["unet_tiny_pair256_pdl"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], pdl=1)
+UNET_CHECKS["unet_tiny_pair256_r1ldg"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], tma_r1=0)
 UNET_CHECKS["svd_steps_tc_graph_pdl"] = _tuned(UNET_CHECKS["svd_steps_tc_graph"], pdl=1)

@@ -35,11 +35,19 @@ def main():
     ap.add_argument("--rounds", type=int, default=5)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-step", action="store_true")
+    ap.add_argument("--tune-a", default="", help="key=value[,key=value] tuning switches set on build a")
+    ap.add_argument("--tune-b", default="", help="... on build b (a and b may then be copies of the same build)")
     a = ap.parse_args()
+    tune = {"a": [kv.split("=") for kv in a.tune_a.split(",") if kv], "b": [kv.split("=") for kv in a.tune_b.split(",") if kv]}
+
+    def use(k):
+        native.use_library(libs[k])
+        for key, val in tune[k]:
+            native.set_tuning(key, int(val))
     dev = torch.device("cuda", 0)
     libs = {"a": a.a, "b": a.b}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    res = {"a": a.a, "b": a.b, "gemm": []}
+    res = {"a": a.a, "b": a.b, "tune": tune, "gemm": []}
     for M, N, K, impl, has_res, geglu in SHAPES:
         x = (torch.randn(M, K, device=dev) * 0.5).half()
         if geglu:
@@ -56,7 +64,7 @@ def main():
         ts = {k: [] for k in libs}
         for rnd in range(a.rounds + 1):
             for k, path in libs.items():
-                native.use_library(path)
+                use(k)
                 native.gemm(out[k], x, w, bias=bias, r1=r1, geglu=geglu, n_store=n_out, impl=impl)
                 torch.cuda.synchronize()
                 e0.record()
@@ -83,7 +91,7 @@ def main():
         outs = {}
         for rnd in range(a.rounds + 1):
             for k, path in libs.items():
-                native.use_library(path)
+                use(k)
                 torch.cuda.synchronize()
                 e0.record()
                 y = x

@@ -38,6 +38,8 @@ Tuning& tuning() {
     v.tma_store = (e != nullptr && e[0] != '0') ? 0 : 1;
     e = getenv("SVDPP_PDL");
     v.pdl = (e != nullptr && e[0] != '0') ? 1 : 0;
+    e = getenv("SVDPP_NO_TMA_R1");
+    v.tma_r1 = (e != nullptr && e[0] != '0') ? 0 : 1;
     return v;
   }();
   return t;
@@ -104,6 +106,7 @@ static int* tuning_slot(const char* key) {
   if (key == nullptr) return nullptr;
   if (strcmp(key, "tma_store") == 0) return &svdpp::tuning().tma_store;
   if (strcmp(key, "pdl") == 0) return &svdpp::tuning().pdl;
+  if (strcmp(key, "tma_r1") == 0) return &svdpp::tuning().tma_r1;
   return nullptr;
 }
 

@@ -45,6 +45,7 @@ int num_sms();
 struct Tuning {
   int tma_store;  // GEMM output tiles through TMA tensor stores
   int pdl;        // programmatic dependent launch on every kernel
+  int tma_r1;     // GEMM residual tile through TMA tensor loads (with tma_store)
 };
 Tuning& tuning();
 

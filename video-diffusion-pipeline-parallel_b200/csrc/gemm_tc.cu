@@ -45,6 +45,9 @@ struct GemmParams {
   // 1: the output tile leaves through TMA tensor stores (tmD) from a 64-byte-swizzled staging tile instead of the
   // per-thread smem -> global copy loop (ncu: that loop held 48 % of the epilogue warps' samples on the K = 320 layers)
   int tma_store;
+  // 1 (TMA-store mode only): the residual tile R1 arrives in the staging tile through TMA tensor loads (tmR, same
+  // boxes and swizzle as tmD) instead of per-thread global loads + st.shared
+  int tma_r1;
 };
 
 // Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
@@ -153,7 +156,7 @@ template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 __global__ void __launch_bounds__(GemmCfg<BN, GEGLU, TWO, EW_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = GemmCfg<BN, GEGLU, TWO, EW_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -162,7 +165,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 3);
+  uint64_t* r1_full = tempty + 3;  // [2] residual tile landed in the staging tile (one per epilogue group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r1_full + 2);
   __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 192);  // [BN] this tile's bias
 
   const int warp = threadIdx.x >> 5;
@@ -179,6 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     if (p.tma_store) tma_prefetch_desc(&tmD);
+    if (p.tma_r1) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -186,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) mbar_init(&tfull[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&r1_full[s], 1);
     for (int s = 0; s < 3; ++s)
       mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS / Cfg::GROUPS);  // pairs: both CTAs' epilogue threads, on the leader
     fence_mbar_init();
@@ -391,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tst) return reinterpret_cast<uint4*>(sCb + (v >> 2) * 8192 + r * 64 + (((v & 3) ^ ((r >> 1) & 3)) << 4));
       return reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8);
     };
+    uint32_t r1_phase = 0;
     int as = Cfg::GROUPS == 2 ? grp : 0;  // with two groups each owns one TMEM stage
     uint32_t aphase = 0;
     int it = grp;
@@ -438,7 +445,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                    : make_uint4(0, 0, 0, 0);
             }
           }
-          if (p.R1 != nullptr) {
+          if (p.R1 != nullptr && p.tma_r1) {
+            // residual tile by TMA: thread 0 waits until the previous round's tensor store has read the staging tile,
+            // then loads the boxes of this round into it; everybody waits on the mbarrier before the chunk loop
+            if (et == 0 && m_base < p.M) {
+              bulk_wait_group_read<0>();
+              int nb = 0;
+#pragma unroll
+              for (int b = 0; b < SW / 32; ++b) nb += (nout0 + b * 32 < p.n_store) ? 1 : 0;
+              mbar_expect_tx(&r1_full[grp], nb * 8192);
+#pragma unroll
+              for (int b = 0; b < SW / 32; ++b)
+                if (nout0 + b * 32 < p.n_store) tma_load_2d(sCb + b * 8192, &tmR, &r1_full[grp], nout0 + b * 32, m_base);
+            }
+          } else if (p.R1 != nullptr) {
             const bool r_vec = (p.ldr1 & 7) == 0 && nout0 + SW <= p.n_store;
             uint4 val[NV];  // all loads in flight at once
 #pragma unroll
@@ -474,6 +494,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (tst && (GEGLU || p.R1 == nullptr) && et == 0) bulk_wait_group_read<0>();  // ... staging tile is free
         epi_bar();
+        if constexpr (!GEGLU) {
+          if (p.R1 != nullptr && p.tma_r1 && m_base < p.M) {
+            mbar_wait(&r1_full[grp], r1_phase, 5);
+            r1_phase ^= 1;
+          }
+        }
         if (rd == 0) {
           if constexpr (Cfg::ROT3)
             mbar_wait(&tfull[it & 1], (it >> 1) & 1, 4);
@@ -717,8 +743,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   // Output through TMA tensor stores: rows of 32 columns (64 bytes) per box, 64-byte swizzle; the tensor map's
   // extents [n_store, M] clip the N padding and the M tail.  Not for the sub-pixel output map (rows scatter), for
   // row pitches that are not 16-byte multiples, or for the 80-column GEGLU round of the 160-wide tile.
-  CUtensorMap tmD = tmB;
+  CUtensorMap tmD = tmB, tmR = tmB;
   p.tma_store = 0;
+  p.tma_r1 = 0;
   if (tuning().tma_store && Cfg::SW % 32 == 0 && p.up <= 1 && (p.ldd & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
     static_assert(Cfg::SW % 32 != 0 || (Cfg::SW / 32) * 8192 <= Cfg::C_BYTES, "swizzled staging tile fits");
@@ -727,18 +754,23 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     uint32_t box[2] = {32, 128};
     if (encode_tmap_f16(&tmD, p.D, 2, dims, str, box, nullptr, 64)) return -5;
     p.tma_store = 1;
+    if (tuning().tma_r1 && !GEGLU && p.R1 != nullptr && (p.ldr1 & 7) == 0 && (reinterpret_cast<uintptr_t>(p.R1) & 15) == 0) {
+      uint64_t rstr[1] = {static_cast<uint64_t>(p.ldr1) * 2};
+      if (encode_tmap_f16(&tmR, p.R1, 2, dims, rstr, box, nullptr, 64)) return -5;
+      p.tma_r1 = 1;
+    }
   }
   if constexpr (TWO) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     int clusters = num_sms() / 2;
     if (pairs < clusters) clusters = pairs;
     SVDPP_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 2, tmA, tmA2, tmB,
-                             tmD, p));
+                             tmD, tmR, p));
     return check_launch("gemm_tc_kernel<pair>");
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  SVDPP_CUDA(launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmA2, tmB, tmD, p));
+  SVDPP_CUDA(launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmA2, tmB, tmD, tmR, p));
   return check_launch("gemm_tc_kernel");
 }
 
