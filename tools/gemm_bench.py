@@ -78,3 +78,8 @@ if __name__ == "__main__":
         for M, N, K in ((230400, 320, 2880), (230400, 320, 960), (230400, 320, 1280), (230400, 320, 640), (57600, 640, 5760),
                         (57600, 640, 2560), (57600, 640, 1920), (57600, 640, 640), (230400, 960, 320), (14400, 1920, 1280)):
             linear_case(M, N, K, (0, 6))
+    if "sweep" in what:  # every tile shape on the N = 320 / 640 / 1280 layers (after an epilogue change the best pick may move)
+        for M, N, K in ((230400, 320, 320), (230400, 320, 640), (230400, 320, 960), (230400, 320, 1280), (230400, 320, 2880),
+                        (57600, 640, 640), (57600, 640, 1280), (57600, 640, 1920), (57600, 640, 2560), (57600, 640, 5760),
+                        (14400, 1280, 1280), (14400, 1280, 3840), (3600, 1280, 1280), (3600, 1280, 3840), (3600, 1280, 11520)):
+            linear_case(M, N, K, (0, 2, 3, 4, 6))
