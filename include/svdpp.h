@@ -37,6 +37,8 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  * produced, never the result (tests/test_gpu_kernels.py runs both settings against the oracle):
  *   "tma_store"  1: GEMM output tiles leave through TMA tensor stores; 0: per-thread copy loop
  *   "tma_r1"     1 (with tma_store): the residual tile R1 reaches the epilogue through TMA tensor loads; 0: per-thread loads
+ *   "epi_dma"    1: GEMMs with 256/128-wide tiles and K <= 64 * "epi_dma_max_kb" (default 5) run their epilogue I/O on a
+ *                   dedicated DMA lane with two staging tiles; 2: wherever possible; 0: never (SVDPP_EPI_DMA, SVDPP_EPI_DMA_MAX_KB)
  *   "pdl"        1: kernels are launched with programmatic stream serialisation (the prologue of kernel N+1
  *                   overlaps the tail of kernel N; every kernel waits on griddepcontrol before touching memory)
  * set returns 0, or -1 for an unknown key; get returns the value, or -1 for an unknown key.

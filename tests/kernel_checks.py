@@ -537,6 +537,20 @@ for _n in ("tc_gemm_linear", "tc_gemm_big", "tc_gemm_split", "pair_gemm_big", "p
            "pair256_gemm_nstore_partial", "pair320_gemm_linear", "pair320_gemm_big", "bn128_gemm_big",
            "pair256_gemm_mtail_odd", "pair320_gemm_mtail_odd"):
     ALL_CHECKS["r1ldg_" + _n] = _tuned(ALL_CHECKS[_n], tma_r1=0)       # residual tile through per-thread loads (TMA loads are the default)
+ALL_CHECKS["tc_gemm_many_tiles"] = lambda: gemm_linear(M=40000, N=640, K=320, impl=0)          # ~8 tiles per CTA
+ALL_CHECKS["pair256_gemm_many_tiles"] = lambda: gemm_linear(M=40000, N=1024, K=320, impl=3)
+ALL_CHECKS["pair320_gemm_many_tiles"] = lambda: gemm_linear(M=70000, N=640, K=320, impl=6)
+ALL_CHECKS["pair_gemm_many_tiles_bias"] = lambda: gemm_linear(M=40000, N=640, K=640, impl=2, epilogue="bias")
+for _n in ("tc_gemm_plain", "tc_gemm_linear", "tc_gemm_split", "pair_gemm_plain", "pair_gemm_linear", "pair_gemm_split",
+           "pair256_gemm_plain", "pair256_gemm_linear", "pair256_gemm_split", "pair256_gemm_nstore_partial",
+           "pair256_gemm_nstore_partial_bias", "bn128_gemm_plain", "bn128_gemm_linear", "bn128_gemm_split",
+           "pair320_gemm_plain", "pair320_gemm_linear", "pair320_gemm_split", "pair256_gemm_mtail_odd",
+           "pair320_gemm_mtail_odd", "tc_conv3x3_w32", "tc_conv3x3_w16", "tc_conv_temporal", "pair_conv3x3_w32",
+           "pair256_conv3x3_w32", "pair320_conv3x3_w32", "bn128_conv3x3_w16", "tc_conv3x3_stride2_w32",
+           "tc_gemm_many_tiles", "pair256_gemm_many_tiles", "pair320_gemm_many_tiles", "pair_gemm_many_tiles_bias"):
+    ALL_CHECKS["dma_" + _n] = _tuned(ALL_CHECKS[_n], epi_dma=2)        # DMA-lane epilogue forced on every tile shape
+for _n in ("pair256_gemm_linear", "pair256_gemm_nstore_partial", "pair256_gemm_many_tiles", "bn128_gemm_linear"):
+    ALL_CHECKS["nodma_" + _n] = _tuned(ALL_CHECKS[_n], epi_dma=0)      # thread-0 epilogue where the DMA lane is the default
 ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
 
 
@@ -620,4 +634,7 @@ UNET_CHECKS = {
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
 UNET_CHECKS["unet_tiny_pair256_pdl"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], pdl=1)
 UNET_CHECKS["unet_tiny_pair256_r1ldg"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], tma_r1=0)
+UNET_CHECKS["unet_tiny_tc_dma"] = _tuned(UNET_CHECKS["unet_tiny_tc"], epi_dma=2)
+UNET_CHECKS["unet_tiny_pair256_dma"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], epi_dma=2)
+UNET_CHECKS["unet_tiny_pair256_nodma"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], epi_dma=0)
 UNET_CHECKS["svd_steps_tc_graph_pdl"] = _tuned(UNET_CHECKS["svd_steps_tc_graph"], pdl=1)

@@ -26,6 +26,10 @@ SHAPES = [  # (M, N, K, impl, residual, geglu)
     (230400, 320, 2880, 6, False, False), (230400, 2560, 320, 3, False, True), (57600, 5120, 640, 3, False, True),
     (14400, 10240, 1280, 3, False, True),
 ]
+SHAPES_PAIR160 = [  # the N = 320 / 640 short-K layers on the 256x160 pair tile (impl 2) instead of the one-CTA 128x160 tile
+    (230400, 320, 320, 2, True, False), (230400, 320, 320, 2, False, False), (57600, 640, 640, 2, True, False),
+    (230400, 320, 640, 2, True, False), (230400, 320, 320, 0, True, False), (57600, 640, 640, 0, True, False),
+]
 
 
 def main():
@@ -35,6 +39,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=5)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-step", action="store_true")
+    ap.add_argument("--shapes", default="net", choices=["net", "pair160"])
     ap.add_argument("--tune-a", default="", help="key=value[,key=value] tuning switches set on build a")
     ap.add_argument("--tune-b", default="", help="... on build b (a and b may then be copies of the same build)")
     a = ap.parse_args()
@@ -48,7 +53,7 @@ def main():
     libs = {"a": a.a, "b": a.b}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {"a": a.a, "b": a.b, "tune": tune, "gemm": []}
-    for M, N, K, impl, has_res, geglu in SHAPES:
+    for M, N, K, impl, has_res, geglu in (SHAPES if a.shapes == "net" else SHAPES_PAIR160):
         x = (torch.randn(M, K, device=dev) * 0.5).half()
         if geglu:
             w = (torch.randn(N, K, device=dev) * K ** -0.5).half()

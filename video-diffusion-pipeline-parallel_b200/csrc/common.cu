@@ -40,6 +40,10 @@ Tuning& tuning() {
     v.pdl = (e != nullptr && e[0] != '0') ? 1 : 0;
     e = getenv("SVDPP_NO_TMA_R1");
     v.tma_r1 = (e != nullptr && e[0] != '0') ? 0 : 1;
+    e = getenv("SVDPP_EPI_DMA");
+    v.epi_dma = e != nullptr ? atoi(e) : 1;
+    e = getenv("SVDPP_EPI_DMA_MAX_KB");
+    v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
     return v;
   }();
   return t;
@@ -107,6 +111,8 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "tma_store") == 0) return &svdpp::tuning().tma_store;
   if (strcmp(key, "pdl") == 0) return &svdpp::tuning().pdl;
   if (strcmp(key, "tma_r1") == 0) return &svdpp::tuning().tma_r1;
+  if (strcmp(key, "epi_dma") == 0) return &svdpp::tuning().epi_dma;
+  if (strcmp(key, "epi_dma_max_kb") == 0) return &svdpp::tuning().epi_dma_max_kb;
   return nullptr;
 }
 

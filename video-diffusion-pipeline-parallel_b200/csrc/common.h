@@ -46,6 +46,8 @@ struct Tuning {
   int tma_store;  // GEMM output tiles through TMA tensor stores
   int pdl;        // programmatic dependent launch on every kernel
   int tma_r1;     // GEMM residual tile through TMA tensor loads (with tma_store)
+  int epi_dma;    // GEMM: DMA-lane epilogue with two staging tiles for short main loops
+  int epi_dma_max_kb;  // ... for K / 64 <= this
 };
 Tuning& tuning();
 

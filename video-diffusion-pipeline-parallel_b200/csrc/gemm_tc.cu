@@ -48,6 +48,10 @@ struct GemmParams {
   // 1 (TMA-store mode only): the residual tile R1 arrives in the staging tile through TMA tensor loads (tmR, same
   // boxes and swizzle as tmD) instead of per-thread global loads + st.shared
   int tma_r1;
+  // 1 (TMA-store mode, one epilogue group, short K): a dedicated DMA lane (warp 3) issues the tensor stores and the
+  // residual loads, and two staging tiles alternate - the second one lives in the last pipeline stages, which a
+  // short main loop does not need.  The epilogue warps never wait for a store to drain or a residual to arrive.
+  int epi_dma;
 };
 
 // Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
@@ -149,6 +153,10 @@ struct GemmCfg {
   // stalls made it the bound.  It uses few registers, so the 256-wide variant runs 16 epilogue warps.
   static constexpr int EPI_WARPS = EW_ ? EW_ : ((GEGLU && BN == 256) ? 16 : 8);
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  // DMA-lane epilogue: bytes of one dense staging tile (SW columns as 32-column boxes) and the pipeline stages the
+  // second tile takes over
+  static constexpr int STG_TILE = (SW / 32) * 8192;
+  static constexpr int STEAL = (STG_TILE + STAGE_BYTES - 1) / STAGE_BYTES;
   static constexpr int THREADS = 128 + EPI_THREADS;
 };
 
@@ -166,7 +174,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* r1_full = tempty + 3;  // [2] residual tile landed in the staging tile (one per epilogue group)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r1_full + 2);
+  uint64_t* stg_full = r1_full + 2;    // [2] DMA-lane epilogue: results of a round are in staging tile b
+  uint64_t* stg_ready = stg_full + 2;  // [2] ... staging tile b is free again (and holds the residual tile, if any)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_ready + 2);
+  static_assert((2 * Cfg::STAGES + 2 + 3 + 2 + 2 + 2) * 8 + 4 <= 192, "barrier area");
+  const int nstages = p.epi_dma ? Cfg::STAGES - Cfg::STEAL : Cfg::STAGES;  // smem ring depth of this launch
   __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 192);  // [BN] this tile's bias
 
   const int warp = threadIdx.x >> 5;
@@ -192,6 +204,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) mbar_init(&tfull[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&r1_full[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&stg_full[s], Cfg::EPI_THREADS / Cfg::GROUPS);
+      mbar_init(&stg_ready[s], 1);
+    }
     for (int s = 0; s < 3; ++s)
       mbar_init(&tempty[s], (TWO ? 2 : 1) * Cfg::EPI_THREADS / Cfg::GROUPS);  // pairs: both CTAs' epilogue threads, on the leader
     fence_mbar_init();
@@ -300,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ++tap;
           }
         }
-        if (++stage == Cfg::STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -350,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma2_commit(&empty[stage]);
           else
             umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == Cfg::STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -366,6 +382,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           aphase ^= 1;
         }
       }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ epilogue DMA lane (p.epi_dma)
+    // Round R of this CTA (tile R / ROUNDS, columns (R % ROUNDS) * SW ...) uses staging tile R & 1.  For every round:
+    // wait until the epilogue warps have staged it, store it, and - once the store has read the tile - hand the tile
+    // to round R + 2, with that round's residual columns already travelling into it.
+    if (p.epi_dma && lane == 0) {
+      const int n_my = work_first < work_total ? (work_total - work_first + work_stride - 1) / work_stride : 0;
+      const int n_rounds = n_my * Cfg::ROUNDS;
+      uint8_t* sbuf[2] = {reinterpret_cast<uint8_t*>(sC), smem + (Cfg::STAGES - Cfg::STEAL) * Cfg::STAGE_BYTES};
+      auto coords = [&](int R, int& m_base, int& nout0) {
+        const int w = work_first + (R / Cfg::ROUNDS) * work_stride;
+        m_base = m_tile_of(w) * Cfg::BM;
+        nout0 = (w % p.n_tiles) * Cfg::NOUT + (R % Cfg::ROUNDS) * Cfg::SW;
+      };
+      auto prepare = [&](int R) {  // staging tile R & 1 is free: start round R's residual loads or just say so
+        int m_base, nout0;
+        coords(R, m_base, nout0);
+        if (p.tma_r1 && m_base < p.M) {
+          int nb = 0;
+#pragma unroll
+          for (int b = 0; b < Cfg::SW / 32; ++b) nb += (nout0 + b * 32 < p.n_store) ? 1 : 0;
+          mbar_expect_tx(&stg_ready[R & 1], nb * 8192);
+#pragma unroll
+          for (int b = 0; b < Cfg::SW / 32; ++b)
+            if (nout0 + b * 32 < p.n_store) tma_load_2d(sbuf[R & 1] + b * 8192, &tmR, &stg_ready[R & 1], nout0 + b * 32, m_base);
+        } else {
+          mbar_arrive(&stg_ready[R & 1]);
+        }
+      };
+      for (int R = 0; R < 2 && R < n_rounds; ++R) prepare(R);
+      for (int R = 0; R < n_rounds; ++R) {
+        int m_base, nout0;
+        coords(R, m_base, nout0);
+        mbar_wait(&stg_full[R & 1], (R >> 1) & 1, 6);
+        if (m_base < p.M) {
+#pragma unroll
+          for (int b = 0; b < Cfg::SW / 32; ++b)
+            if (nout0 + b * 32 < p.n_store) tma_store_2d(&tmD, sbuf[R & 1] + b * 8192, nout0 + b * 32, m_base);
+          bulk_commit_group();
+        }
+        if (R + 2 < n_rounds) {
+          bulk_wait_group_read<0>();
+          prepare(R + 2);
+        }
+      }
+      bulk_wait_group<0>();  // the staging tiles must outlive the last store
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -397,6 +460,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tst) return reinterpret_cast<uint4*>(sCb + (v >> 2) * 8192 + r * 64 + (((v & 3) ^ ((r >> 1) & 3)) << 4));
       return reinterpret_cast<uint4*>(sC + r * Cfg::C_PITCH + v * 8);
     };
+    if (p.epi_dma) {
+      // ---- DMA-lane mode (one group): no named barrier inside a tile, no wait for stores or residual loads
+      if constexpr (!GEGLU && Cfg::GROUPS == 1) {
+        uint8_t* sbuf[2] = {sCb, smem + (Cfg::STAGES - Cfg::STEAL) * Cfg::STAGE_BYTES};
+        int as = 0, it = 0, rc = 0;
+        uint32_t aphase = 0;
+        for (int w = work_first; w < work_total; w += work_stride, ++it) {
+          const int m_tile = m_tile_of(w);
+          const int n_tile = w % p.n_tiles;
+          const int m_base = m_tile * Cfg::BM;
+          const int m = m_base + row;
+          const bool m_ok = m < p.M;
+          __half* sB = sBias + (it & 1) * BN;  // two bias tiles: tile it + 1 may be staged while stragglers finish tile it
+          if (et < BN / 8) {
+            uint4 bv = make_uint4(0, 0, 0, 0);
+            if (p.bias != nullptr) bv = *reinterpret_cast<const uint4*>(p.bias + n_tile * BN + et * 8);
+            *reinterpret_cast<uint4*>(sB + et * 8) = bv;
+          }
+          const __half* rv_row = nullptr;
+          if (p.rowvec != nullptr && m_ok) {
+            const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
+            rv_row = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN;
+          }
+          const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(we * 32) << 16);
+          epi_bar();  // bias tile visible; everybody has left tile it - 1, so its bias tile may be rewritten by tile it + 1
+#pragma unroll 1
+          for (int rd = 0; rd < Cfg::ROUNDS; ++rd, ++rc) {
+            const int col0 = rd * SW;
+            const int rot_buf = (2 * it + rd) % 3;
+            const uint32_t taddr = Cfg::ROT3 ? taddr_base + rot_buf * Cfg::MMA_N - col0 : taddr_base + as * Cfg::ACC_STRIDE;
+            const int nout0 = n_tile * Cfg::NOUT + col0;
+            uint8_t* sb = sbuf[rc & 1];
+            auto svec = [&](int v) -> uint4* {  // 16-byte vector v of this thread's staged row (64-byte swizzle of tmD / tmR)
+              return reinterpret_cast<uint4*>(sb + (v >> 2) * 8192 + row * 64 + (((v & 3) ^ ((row >> 1) & 3)) << 4));
+            };
+            uint4 rvv[NCH][CW / 8];
+            if (rv_row != nullptr) {
+#pragma unroll
+              for (int ci = 0; ci < NCH; ++ci) {
+                const int c = half + WPQ * ci;
+#pragma unroll
+                for (int hlf = 0; hlf < CW / 8; ++hlf)
+                  rvv[ci][hlf] = (nout0 + c * CW < p.n_store)
+                                     ? *reinterpret_cast<const uint4*>(rv_row + col0 + c * CW + hlf * 8)
+                                     : make_uint4(0, 0, 0, 0);
+              }
+            }
+            mbar_wait(&stg_ready[rc & 1], (rc >> 1) & 1, 7);  // staging tile free, residual columns landed
+            if (rd == 0) {
+              if constexpr (Cfg::ROT3)
+                mbar_wait(&tfull[it & 1], (it >> 1) & 1, 4);
+              else
+                mbar_wait(&tfull[as], aphase, 4);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+              const int c = half + WPQ * ci;
+              uint32_t v[CW];
+              tmem_ld_x16(taddr + col0 + c * CW, v);
+              tmem_ld_wait();
+              const int nout = nout0 + c * CW;
+              float y[CW];
+#pragma unroll
+              for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]);
+              {
+                float b8[8];
+#pragma unroll
+                for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                  load8(sB + col0 + c * CW + hlf * 8, b8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+                }
+              }
+              if (rv_row != nullptr) {
+#pragma unroll
+                for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&rvv[ci][hlf]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    y[hlf * 8 + 2 * j] += f.x;
+                    y[hlf * 8 + 2 * j + 1] += f.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < CW; ++j) y[j] *= p.alpha;
+              if (p.R1 != nullptr) {
+                float b8[8];
+#pragma unroll
+                for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                  load8(reinterpret_cast<const __half*>(svec((c * CW) / 8 + hlf)), b8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
+                }
+              }
+              if (p.R2 != nullptr && m_ok && nout < p.n_store) {
+                float b8[8];
+#pragma unroll
+                for (int hlf = 0; hlf < CW / 8; ++hlf) {
+                  load8(p.R2 + static_cast<long long>(m) * p.ldr2 + nout + hlf * 8, b8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
+                }
+              }
+              __align__(16) __half o[CW];
+#pragma unroll
+              for (int j = 0; j < CW; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
+              const uint4* o4 = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+              for (int q = 0; q < CW / 8; ++q) *svec((c * CW) / 8 + q) = o4[q];
+            }
+            fence_proxy_async_smem();  // staged results -> visible to the TMA engine
+            if constexpr (Cfg::ROT3) {
+              tc_fence_before();
+              mbar_arrive_cluster(&tempty[rot_buf], 0);
+            } else if (rd == Cfg::ROUNDS - 1) {
+              tc_fence_before();
+              if constexpr (TWO)
+                mbar_arrive_cluster(&tempty[as], 0);
+              else
+                mbar_arrive(&tempty[as]);
+            }
+            mbar_arrive(&stg_full[rc & 1]);  // the DMA lane stores the tile
+          }
+          if (++as == Cfg::NACC) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+      }
+    } else {
     uint32_t r1_phase = 0;
     int as = Cfg::GROUPS == 2 ? grp : 0;  // with two groups each owns one TMEM stage
     uint32_t aphase = 0;
@@ -633,6 +829,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (tst && et == 0) bulk_wait_group<0>();  // the staging tile must outlive the last tensor store
+    }  // !p.epi_dma
   }
 
   tc_fence_before();
@@ -746,6 +943,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   CUtensorMap tmD = tmB, tmR = tmB;
   p.tma_store = 0;
   p.tma_r1 = 0;
+  p.epi_dma = 0;
   if (tuning().tma_store && Cfg::SW % 32 == 0 && p.up <= 1 && (p.ldd & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
     static_assert(Cfg::SW % 32 != 0 || (Cfg::SW / 32) * 8192 <= Cfg::C_BYTES, "swizzled staging tile fits");
@@ -759,6 +957,13 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
       if (encode_tmap_f16(&tmR, p.R1, 2, dims, rstr, box, nullptr, 64)) return -5;
       p.tma_r1 = 1;
     }
+    // DMA-lane epilogue: measured (tools/ab_lib.py) +19.5 % on the level-0 qkv projection (256x256 pair tiles, K = 320,
+    // 4 of 5 stages left), but 0.80-0.97x where the second staging tile costs TWO stages (160/320-wide tiles: 3 left)
+    // and 0.98x at K = 640 - so by default only where one stage is given up and the main loop is at most 5 k-blocks.
+    // epi_dma = 2 forces it wherever it is possible (tests).
+    const bool dma_ok = !GEGLU && Cfg::GROUPS == 1 && (p.R1 == nullptr || p.tma_r1) && Cfg::STAGES - Cfg::STEAL >= 2;
+    if (dma_ok && (tuning().epi_dma >= 2 || (tuning().epi_dma == 1 && Cfg::STEAL == 1 && p.num_kb <= tuning().epi_dma_max_kb)))
+      p.epi_dma = 1;
   }
   if constexpr (TWO) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
