@@ -228,6 +228,9 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its banner ("NCCL version ...", NCCL_DEBUG >= VERSION) to stdout by default: keep stdout to the
+        # ONE JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     F_, H, W, T = args.frames, args.latent_height, args.latent_width, args.denoise_steps
