@@ -221,6 +221,12 @@ def main() -> None:
     from vdpp_b200.models.native_unet import flops_per_forward
     from vdpp_b200.pipeline import LatentSpec, PipelineConfig, PipelineStage, stage_sizes
 
+    # stdout carries exactly ONE JSON line (the contract).  NCCL prints its banner ("NCCL version ...") with printf on
+    # file descriptor 1, so fd 1 is pointed at stderr for the whole run and the line goes out through a saved copy.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,9 +234,6 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its banner ("NCCL version ...", NCCL_DEBUG >= VERSION) to stdout by default: keep stdout to the
-        # ONE JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     F_, H, W, T = args.frames, args.latent_height, args.latent_width, args.denoise_steps
@@ -460,7 +463,7 @@ def main() -> None:
             result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                       "sample": f"failed: {type(e).__name__}: {e}"}
     if rank == 0:
-        print(json.dumps(result))
+        print(json.dumps(result), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
