@@ -55,3 +55,18 @@ def test_no_cpu_path():
     with pytest.raises(native.NativeError):
         native.layernorm(torch.empty(2, 8, dtype=torch.float16), torch.empty(2, 8, dtype=torch.float16),
                          torch.empty(8, dtype=torch.float16), torch.empty(8, dtype=torch.float16))
+
+
+def test_tuning_switches_roundtrip():
+    # svdpp_set_tuning / svdpp_get_tuning are host-only: defaults, round trip, unknown keys
+    assert native.get_tuning("tma_store") == 1 and native.get_tuning("tma_r1") == 1
+    assert native.get_tuning("pdl") == 0 and native.get_tuning("epi_dma") == 1
+    old = native.set_tuning("pdl", 1)
+    try:
+        assert old == 0 and native.get_tuning("pdl") == 1
+    finally:
+        native.set_tuning("pdl", old)
+    with pytest.raises(native.NativeError):
+        native.get_tuning("no_such_switch")
+    with pytest.raises(native.NativeError):
+        native.set_tuning("no_such_switch", 1)
