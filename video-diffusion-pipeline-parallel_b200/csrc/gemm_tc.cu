@@ -4,9 +4,13 @@
 //   warp 0      TMA producer   global -> 128B-swizzled smem ring (A tile 128x64, B tile BNx64)
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages)
-//   warps 4..11 epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16, staged
-//               through padded smem so residual loads and output stores are fully coalesced;
-//               two warps per TMEM lane quarter, each taking every other column chunk
+//   warp 3      epilogue DMA lane (p.epi_dma): issues the output tensor stores and residual tensor loads
+//   warps 4..11 epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16 into a staging tile in
+//               smem; two warps per TMEM lane quarter, each taking every other column chunk.  The staging tile is
+//               kept in the 64-byte swizzle of a tensor map over the output and leaves through TMA tensor stores
+//               (one thread per epilogue group, or the DMA lane); the residual tile R1 arrives in it through TMA
+//               tensor loads.  A padded staging tile with per-thread coalesced copies remains for outputs the
+//               tensor map cannot describe (sub-pixel scatter, rows that are not 16-byte multiples).
 // The two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Convolutions never materialise im2col: for tap (dw,dh,df) the producer loads the activation
 // window shifted by the tap through a 5-D tensor map [C, W, H, F, B]; TMA zero-fills the halo.
