@@ -140,6 +140,7 @@ def main():
     if a.graph:
         res["graph_ms"] = {}
         model.use_cuda_graph = True
+        ref2 = None
         for tst, pdl in settings:
             native.set_tuning("tma_store", tst)
             native.set_tuning("pdl", pdl)
@@ -147,8 +148,8 @@ def main():
             try:
                 time_steps(model, x, a.steps)               # warm-up + capture of steps 0..steps-1
                 ms, y = time_steps(model, x, a.steps)
-                same = bool(torch.equal(ref2, y)) if "ref2" in locals() else True
-                ref2 = y if "ref2" not in locals() else ref2
+                same = ref2 is None or bool(torch.equal(ref2, y))
+                ref2 = y if ref2 is None else ref2
                 res["graph_ms"][f"tma{tst}_pdl{pdl}"] = round(ms, 3)
                 res["identical"] = res["identical"] and same
                 print(f"graph tma_store={tst} pdl={pdl}: {ms:.3f} ms/step identical={same}", flush=True)
