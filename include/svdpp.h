@@ -39,6 +39,9 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   "tma_r1"     1 (with tma_store): the residual tile R1 reaches the epilogue through TMA tensor loads; 0: per-thread loads
  *   "epi_dma"    1: GEMMs with 256/128-wide tiles and K <= 64 * "epi_dma_max_kb" (default 5) run their epilogue I/O on a
  *                   dedicated DMA lane with two staging tiles; 2: wherever possible; 0: never (SVDPP_EPI_DMA, SVDPP_EPI_DMA_MAX_KB)
+ *   "splitk"     1: impl 6 splits the tiles of a short last wave along K when the descriptor carries splitk_ws; 0: never
+ *                   ("splitk_min_kb": fewest 64-wide k-blocks a slice may get, default 4; "splitk_min_total_kb": only for
+ *                   K / 64 >= this, default 64)
  *   "pdl"        1: kernels are launched with programmatic stream serialisation (the prologue of kernel N+1
  *                   overlaps the tail of kernel N; every kernel waits on griddepcontrol before touching memory)
  * set returns 0, or -1 for an unknown key; get returns the value, or -1 for an unknown key.
@@ -87,6 +90,11 @@ typedef struct svdpp_gemm_desc {
    * "nearest-neighbour 2x upsample + Conv2d 3x3" as four 2x2-tap convolutions on the low-resolution input, one per
    * output parity, with pre-summed weights: 4/9 of the FLOPs and no upsampled tensor.  0 or 1: off. */
   int32_t out_up, out_up_y, out_up_x;
+  /* optional scratch for the split-K tail of impl 6 (256x320 pair tiles): when the last wave of tiles would keep fewer
+   * than half of the CTA pairs busy, its tiles are split along K over the idle pairs and reduced through this buffer
+   * (fp32, slice order: deterministic).  >= 4096 + 74 * 327680 bytes covers every shape; its first 4096 bytes are
+   * counters that must be zero before the first use (the kernel re-arms them).  NULL: no split. */
+  void* splitk_ws; int64_t splitk_ws_bytes;
 } svdpp_gemm_desc;
 
 /* impl selects the tile shape of the tcgen05 kernel (Wt must be padded to a multiple of the tile's N):

@@ -551,6 +551,18 @@ for _n in ("tc_gemm_plain", "tc_gemm_linear", "tc_gemm_split", "pair_gemm_plain"
     ALL_CHECKS["dma_" + _n] = _tuned(ALL_CHECKS[_n], epi_dma=2)        # DMA-lane epilogue forced on every tile shape
 for _n in ("pair256_gemm_linear", "pair256_gemm_nstore_partial", "pair256_gemm_many_tiles", "bn128_gemm_linear"):
     ALL_CHECKS["nodma_" + _n] = _tuned(ALL_CHECKS[_n], epi_dma=0)      # thread-0 epilogue where the DMA lane is the default
+# split-K tail of the 256x320 pair tiles: 80 / 86 / 111 pair tiles on 74 pairs -> 6 / 12 / 37 tiles in the last wave
+ALL_CHECKS["pair320_splitk_12way"] = lambda: gemm_linear(M=20480, N=320, K=3072, impl=6)
+ALL_CHECKS["pair320_splitk_5way"] = lambda: gemm_linear(M=20480, N=320, K=1280, impl=6)
+ALL_CHECKS["pair320_splitk_6way_bias"] = lambda: gemm_linear(M=11008, N=640, K=1920, impl=6, epilogue="bias")
+ALL_CHECKS["pair320_splitk_2way_mtail"] = lambda: gemm_linear(M=28400, N=320, K=640, impl=6)
+ALL_CHECKS["pair320_splitk_conv"] = lambda: conv3x3(B=1, Fr=10, H=64, W=32, C=128, Cout=320, impl=6)
+ALL_CHECKS["pair320_splitk_conv_temporal"] = lambda: conv_temporal(B=2, Fr=5, H=64, W=32, C=320, impl=6)
+for _n in ("pair320_splitk_12way", "pair320_splitk_5way", "pair320_splitk_6way_bias", "pair320_splitk_2way_mtail",
+           "pair320_splitk_conv", "pair320_splitk_conv_temporal"):
+    ALL_CHECKS[_n] = _tuned(ALL_CHECKS[_n], splitk_min_total_kb=1)      # small K here: lift the K threshold of the default rule
+for _n in ("pair320_splitk_12way", "pair320_splitk_conv"):
+    ALL_CHECKS["nosplit_" + _n] = _tuned(ALL_CHECKS[_n], splitk=0)
 ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
 
 

@@ -23,7 +23,8 @@ SHAPES = [  # (M, N, K, impl, residual, geglu)
     (230400, 320, 320, 0, True, False), (230400, 320, 320, 0, False, False), (230400, 1024, 320, 3, False, False),
     (230400, 320, 1280, 6, True, False), (57600, 640, 640, 0, True, False), (57600, 2048, 640, 3, False, False),
     (57600, 640, 2560, 6, True, False), (14400, 1280, 1280, 3, True, False), (14400, 1280, 5120, 3, True, False),
-    (230400, 320, 2880, 6, False, False), (230400, 2560, 320, 3, False, True), (57600, 5120, 640, 3, False, True),
+    (230400, 320, 2880, 6, False, False), (57600, 640, 5760, 6, False, False), (230400, 320, 5760, 6, True, False),
+    (230400, 2560, 320, 3, False, True), (57600, 5120, 640, 3, False, True),
     (14400, 10240, 1280, 3, False, True),
 ]
 SHAPES_PAIR160 = [  # the N = 320 / 640 short-K layers on the 256x160 pair tile (impl 2) instead of the one-CTA 128x160 tile

@@ -42,6 +42,10 @@ Tuning& tuning() {
     v.tma_r1 = (e != nullptr && e[0] != '0') ? 0 : 1;
     e = getenv("SVDPP_EPI_DMA");
     v.epi_dma = e != nullptr ? atoi(e) : 1;
+    e = getenv("SVDPP_NO_SPLITK");
+    v.splitk = (e != nullptr && e[0] != '0') ? 0 : 1;
+    v.splitk_min_kb = 4;
+    v.splitk_min_total_kb = 64;
     e = getenv("SVDPP_EPI_DMA_MAX_KB");
     v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
     return v;
@@ -113,6 +117,9 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "tma_r1") == 0) return &svdpp::tuning().tma_r1;
   if (strcmp(key, "epi_dma") == 0) return &svdpp::tuning().epi_dma;
   if (strcmp(key, "epi_dma_max_kb") == 0) return &svdpp::tuning().epi_dma_max_kb;
+  if (strcmp(key, "splitk") == 0) return &svdpp::tuning().splitk;
+  if (strcmp(key, "splitk_min_kb") == 0) return &svdpp::tuning().splitk_min_kb;
+  if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   return nullptr;
 }
 

@@ -48,6 +48,9 @@ struct Tuning {
   int tma_r1;     // GEMM residual tile through TMA tensor loads (with tma_store)
   int epi_dma;    // GEMM: DMA-lane epilogue with two staging tiles for short main loops
   int epi_dma_max_kb;  // ... for K / 64 <= this
+  int splitk;          // GEMM impl 6: split-K tail when the descriptor carries a workspace
+  int splitk_min_kb;   // ... fewest k-blocks per slice
+  int splitk_min_total_kb;  // ... only for K / 64 >= this (the tail machinery costs ~20 us, a tile ~0.45 us per k-block)
 };
 Tuning& tuning();
 

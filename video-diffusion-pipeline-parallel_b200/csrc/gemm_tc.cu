@@ -56,6 +56,14 @@ struct GemmParams {
   // residual loads, and two staging tiles alternate - the second one lives in the last pipeline stages, which a
   // short main loop does not need.  The epilogue warps never wait for a store to drain or a residual to arrive.
   int epi_dma;
+  // Split-K tail (256x320 pair tiles only).  The tiles of the last, partial wave (sk_r of them, after sk_full tiles
+  // in full waves) are each computed by `splitk` CTA pairs over disjoint K ranges; the fp32 partial accumulators meet
+  // in the workspace sk_ws, and once a tile's partials are all there (counter in sk_cnt) every participating CTA
+  // finishes a share of its 16-column chunks, summing the partials in slice order (deterministic).
+  int splitk, sk_r, sk_full;
+  float* sk_ws;
+  unsigned* sk_cnt;
+  long long sk_ws_bytes;  // host side only: size of the caller's scratch (counters + partials)
 };
 
 // Exact-erf GELU (torch F.gelu, approximate='none') in 10 instructions and ONE MUFU:  gelu(x) = max(x,0) - a*Phi(-a),
@@ -191,7 +199,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int cta_rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
   const int work_first = TWO ? (blockIdx.x >> 1) : blockIdx.x;
   const int work_stride = TWO ? (gridDim.x >> 1) : gridDim.x;
-  const int work_total = TWO ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int work_total_all = TWO ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  // with a split-K tail the regular loops cover the full waves only; this CTA pair's share of the tail is one extra
+  // item (tile tail_w, k-blocks [tail_kb0, tail_kb1)) appended to the producer's and the MMA issuer's loops
+  const int work_total = (Cfg::ROT3 && p.splitk > 1) ? p.sk_full : work_total_all;
+  const int n_full_items = work_first < work_total ? (work_total - work_first + work_stride - 1) / work_stride : 0;
+  int tail_w = -1, tail_kb0 = 0, tail_kb1 = 0, tail_j = 0, tail_s = 0;
+  if constexpr (Cfg::ROT3) {
+    if (p.splitk > 1) {
+      tail_j = work_first / p.splitk;
+      tail_s = work_first - tail_j * p.splitk;
+      if (tail_j < p.sk_r) {
+        tail_w = p.sk_full + tail_j;
+        tail_kb0 = (tail_s * p.num_kb) / p.splitk;
+        tail_kb1 = ((tail_s + 1) * p.num_kb) / p.splitk;
+      }
+    }
+  }
+  const int n_items = n_full_items + (tail_w >= 0 ? 1 : 0);
   auto m_tile_of = [&](int w) { return TWO ? 2 * (w / p.n_tiles) + cta_rank : w / p.n_tiles; };
 
   if (warp == 0 && lane == 0) {
@@ -245,7 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ahead via cp.async.bulk.prefetch.tensor lowered throughput by ~40 % on B200.)
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = work_first; w < work_total; w += work_stride) {
+    for (int item = 0; item < n_items; ++item) {
+      const bool is_tail = item >= n_full_items;
+      const int w = is_tail ? tail_w : work_first + item * work_stride;
+      const int kb_begin = is_tail ? tail_kb0 : 0, kb_end = is_tail ? tail_kb1 : p.num_kb;
       const int m0 = m_tile_of(w) * Cfg::BM;
       const int n0 = (w % p.n_tiles) * BN + cta_rank * Cfg::B_ROWS;
       int cw = 0, ch = 0, cf = 0, cb = 0;
@@ -270,7 +298,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       int tap = 0, kc = 0;  // k-block = (tap, kc)
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      if (p.conv && kb_begin > 0) {
+        tap = kb_begin / p.cpk;
+        kc = kb_begin - tap * p.cpk;
+      }
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
         if (lane == 0) {
@@ -335,7 +367,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0;
       uint32_t aphase = 0;
       int it = 0;  // tiles done by this CTA pair (ROT3 buffer rotation)
-      for (int w = work_first; w < work_total; w += work_stride, ++it) {
+      for (int item = 0; item < n_items; ++item, ++it) {
+        const bool is_tail = item >= n_full_items;
+        const int kb_begin = is_tail ? tail_kb0 : 0, kb_end = is_tail ? tail_kb1 : p.num_kb;
         uint32_t d_tmem, d_tmem2 = 0;
         if constexpr (Cfg::ROT3) {
           const int h0 = 2 * it, h1 = h0 + 1;  // half-tile sequence numbers; buffer = h % 3, its use count = h / 3
@@ -348,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
         }
         tc_fence_after();
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -358,12 +392,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
             if constexpr (TWO) {
-              umma2_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma2_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
               if constexpr (Cfg::MMAS == 2)
                 umma2_f16(d_tmem2, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
-                          idesc, (kb | k) != 0 ? 1u : 0u);
+                          idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             } else {
-              umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             }
           }
           if constexpr (TWO)
@@ -393,8 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // wait until the epilogue warps have staged it, store it, and - once the store has read the tile - hand the tile
     // to round R + 2, with that round's residual columns already travelling into it.
     if (p.epi_dma && lane == 0) {
-      const int n_my = work_first < work_total ? (work_total - work_first + work_stride - 1) / work_stride : 0;
-      const int n_rounds = n_my * Cfg::ROUNDS;
+      const int n_rounds = n_full_items * Cfg::ROUNDS;  // the split-K tail item does not go through the staging tiles
       uint8_t* sbuf[2] = {reinterpret_cast<uint8_t*>(sC), smem + (Cfg::STAGES - Cfg::STEAL) * Cfg::STAGE_BYTES};
       auto coords = [&](int R, int& m_base, int& nout0) {
         const int w = work_first + (R / Cfg::ROUNDS) * work_stride;
@@ -834,6 +867,151 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (tst && et == 0) bulk_wait_group<0>();  // the staging tile must outlive the last tensor store
     }  // !p.epi_dma
+    if constexpr (Cfg::ROT3) {
+      if (tail_w >= 0) {
+        // ---- split-K tail: this pair computed k-blocks [tail_kb0, tail_kb1) of tile tail_w
+        const int S = p.splitk;
+        const int it = n_full_items;  // sequence number of this tile on this pair (TMEM buffer rotation)
+        const int m_base = m_tile_of(tail_w) * Cfg::BM;
+        const int n_tile = tail_w % p.n_tiles;
+        const int m = m_base + row;
+        const uint32_t taddr_base = tmem_base + (static_cast<uint32_t>(we * 32) << 16);
+        constexpr int NCHUNK = BN / 16;                       // 16-column chunks of the tile
+        constexpr size_t PART = size_t(NCHUNK) * Cfg::BM * 16;  // floats of one CTA's partial, laid out [chunk][row][16]
+        mbar_wait(&tfull[it & 1], (it >> 1) & 1, 4);
+        tc_fence_after();
+        float* mine = p.sk_ws + (size_t((tail_j * S + tail_s) * 2 + cta_rank)) * PART;
+#pragma unroll 1
+        for (int c = half; c < NCHUNK; c += WPQ) {
+          const int col = c * 16;
+          const uint32_t tcol = static_cast<uint32_t>(((2 * it + (col >= Cfg::MMA_N ? 1 : 0)) % 3) * Cfg::MMA_N +
+                                                      (col >= Cfg::MMA_N ? col - Cfg::MMA_N : col));
+          uint32_t v[16];
+          tmem_ld_x16(taddr_base + tcol, v);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(mine + (size_t(c) * Cfg::BM + row) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __threadfence();  // partial visible device-wide before the arrival below
+        epi_bar();
+        unsigned* cnt = p.sk_cnt + (tail_j * 2 + cta_rank) * 2;  // [0] arrivals, [1] departures
+        if (et == 0) {
+          atomicAdd(cnt, 1u);
+          while (*reinterpret_cast<volatile unsigned*>(cnt) < static_cast<unsigned>(S)) __nanosleep(64);
+          __threadfence();
+        }
+        epi_bar();
+        // every slice finishes the chunks c = slice, slice + S, ... ; the two warps of a lane quarter alternate
+        int k_own = 0;
+#pragma unroll 1
+        for (int c = tail_s; c < NCHUNK; c += S, ++k_own) {
+          if ((k_own % WPQ) != half) continue;
+          float y[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = 0.f;
+          // four slices' vectors in flight at a time (one L2 round trip per group of four, not per slice); added in
+          // slice order, so the result does not depend on arrival order
+          for (int t0 = 0; t0 < S; t0 += 4) {
+            float4 f[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int t = t0 + u < S ? t0 + u : S - 1;  // clamped loads are discarded below
+              const float4* src = reinterpret_cast<const float4*>(
+                  p.sk_ws + (size_t((tail_j * S + t) * 2 + cta_rank)) * PART + (size_t(c) * Cfg::BM + row) * 16);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) f[u][q] = __ldcg(src + q);  // written by other SMs: bypass L1
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (t0 + u < S) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  y[4 * q] += f[u][q].x;
+                  y[4 * q + 1] += f[u][q].y;
+                  y[4 * q + 2] += f[u][q].z;
+                  y[4 * q + 3] += f[u][q].w;
+                }
+              }
+            }
+          }
+          const int col = c * 16;
+          const int nout = n_tile * Cfg::NOUT + col;
+          if (m < p.M && nout < p.n_store) {
+            float b8[8];
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(p.bias + n_tile * BN + col + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+              }
+            }
+            if (p.rowvec != nullptr) {
+              const int rr = ((m / p.rv_hw) / p.rv_div) % p.rv_mod;
+              const __half* rv = p.rowvec + static_cast<long long>(rr) * p.rv_ld + n_tile * BN + col;
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                load8(rv + hlf * 8, b8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += b8[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] *= p.alpha;
+            const bool full16 = nout + 16 <= p.n_store;
+            if (p.R1 != nullptr) {
+              const __half* r = p.R1 + static_cast<long long>(m) * p.ldr1 + nout;
+              if (full16 && (p.ldr1 & 7) == 0) {
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                  load8(r + hlf * 8, b8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta1 * b8[j];
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (nout + j < p.n_store) y[j] += p.beta1 * __half2float(r[j]);
+              }
+            }
+            if (p.R2 != nullptr) {
+              const __half* r = p.R2 + static_cast<long long>(m) * p.ldr2 + nout;
+              if (full16 && (p.ldr2 & 7) == 0) {
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                  load8(r + hlf * 8, b8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[hlf * 8 + j] += p.beta2 * b8[j];
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (nout + j < p.n_store) y[j] += p.beta2 * __half2float(r[j]);
+              }
+            }
+            __align__(16) __half o[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<__half2*>(&o[j]) = __floats2half2_rn(y[j], y[j + 1]);
+            __half* dst = p.D + out_row(p, m) * p.ldd + nout;
+            if (full16 && (p.ldd & 7) == 0) {
+              reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
+              reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (nout + j < p.n_store) dst[j] = o[j];
+            }
+          }
+        }
+        // the last CTA through re-arms the counters for the next launch that uses this workspace
+        epi_bar();
+        if (et == 0) {
+          if (atomicAdd(cnt + 1, 1u) == static_cast<unsigned>(S - 1)) {
+            cnt[0] = 0u;
+            cnt[1] = 0u;
+            __threadfence();
+          }
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -973,6 +1151,29 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     int clusters = num_sms() / 2;
     if (pairs < clusters) clusters = pairs;
+    p.splitk = 0;
+    if constexpr (Cfg::ROT3) {
+      // split-K tail: r tiles left for a last wave of `clusters` pairs -> each tile on S = clusters / r pairs
+      const int full_waves = pairs / clusters, r = pairs % clusters;
+      // measured (tools/tail_probe.py): the tail machinery (slice pipeline start, partial dump, cross-CTA wait, fix-up)
+      // costs about 20-25 us whatever K is, an unsplit last wave one tile time (~0.5 us per k-block): K = 5760 at level 1
+      // 434 -> 393 us, K = 2880 379 -> 369 us, K <= 2560 slower - hence the K threshold
+      if (tuning().splitk && p.sk_ws != nullptr && r > 0 && full_waves >= 1 && p.num_kb >= tuning().splitk_min_total_kb) {
+        int S = clusters / r;
+        const int min_kb = tuning().splitk_min_kb > 0 ? tuning().splitk_min_kb : 1;
+        if (S > p.num_kb / min_kb) S = p.num_kb / min_kb;
+        if (S > BN / 16) S = BN / 16;
+        const long long part_bytes = 2LL * (BN / 16) * Cfg::BM * 16 * 4;  // both CTAs of a pair
+        if (S >= 2 && 4096 + static_cast<long long>(r) * S * part_bytes <= p.sk_ws_bytes &&
+            static_cast<size_t>(r) * 4 * sizeof(unsigned) <= 4096) {
+          p.splitk = S;
+          p.sk_r = r;
+          p.sk_full = full_waves * clusters;
+          p.sk_cnt = reinterpret_cast<unsigned*>(p.sk_ws);
+          p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(p.sk_ws) + 4096);
+        }
+      }
+    }
     SVDPP_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 2, tmA, tmA2, tmB,
                              tmD, tmR, p));
     return check_launch("gemm_tc_kernel<pair>");
@@ -1026,6 +1227,8 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   p.D = static_cast<__half*>(d->D);
   p.ldd = d->ldd;
   p.n_store = n_store;
+  p.sk_ws = static_cast<float*>(d->splitk_ws);
+  p.sk_ws_bytes = d->splitk_ws != nullptr ? d->splitk_ws_bytes : 0;
   p.m_tiles = (d->M + 127) / 128;
   p.n_tiles = d->N / BN;
   {

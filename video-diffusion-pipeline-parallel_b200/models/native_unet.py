@@ -142,6 +142,7 @@ class NativeUNet(nn.Module):
         self._pos_cache: Dict[Tuple[str, int], torch.Tensor] = {}
         self._gn_ws: Optional[torch.Tensor] = None
         self._sms: Optional[int] = None
+        native.splitk_workspace(self.device_)    # scratch of the split-K tail (256x320 tiles, long K): before any graph capture
         self._build()
         self._sd = None
 

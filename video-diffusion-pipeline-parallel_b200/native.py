@@ -53,6 +53,7 @@ class GemmDesc(C.Structure):
         ("n_store", C.c_int32),
         ("conv_stride", C.c_int32), ("cHin", C.c_int32), ("cWin", C.c_int32),
         ("out_up", C.c_int32), ("out_up_y", C.c_int32), ("out_up_x", C.c_int32),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
     ]
 
 
@@ -201,11 +202,26 @@ def _fill_taps(desc: GemmDesc, taps: Sequence[Tuple[int, int, int]]) -> None:
         desc.taps[i][0], desc.taps[i][1], desc.taps[i][2], desc.taps[i][3] = dw, dh, df, 0
 
 
+SPLITK_WS_BYTES = 4096 + 74 * 2 * 20 * 128 * 16 * 4   # counters + one fp32 partial per CTA pair (include/svdpp.h)
+_splitk_ws = {}
+
+
+def splitk_workspace(device) -> torch.Tensor:
+    """Per-device scratch of the split-K tail of impl 6 (zeroed once; the kernel re-arms its counters).  All GEMMs
+    of a process run on one stream, so one buffer serves them all.  Create it outside CUDA-graph capture."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _splitk_ws:
+        _splitk_ws[key] = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=dev)
+    return _splitk_ws[key]
+
+
 def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=None,
          conv_dims: Optional[Tuple[int, int, int, int, int]] = None, taps=None,
          rowvec=None, rv_hw=1, rv_div=1, rv_mod=0, r1=None, beta1=1.0, r2=None, beta2=1.0, alpha=1.0,
          geglu=False, n_store=0, impl=0, conv_stride: int = 1,
-         conv_in_hw: Optional[Tuple[int, int]] = None, out_up: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+         conv_in_hw: Optional[Tuple[int, int]] = None, out_up: Optional[Tuple[int, int, int]] = None,
+         splitk_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out = epilogue(A @ w.T)``; see ``svdpp_gemm_desc`` in include/svdpp.h.
 
     ``a``: [M, K] (row stride may exceed K) or, with ``conv_dims=(B,F,H,W,C)``, the contiguous
@@ -251,6 +267,12 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
     d.alpha = alpha
     d.geglu = 1 if geglu else 0
     d.D, d.ldd = out.data_ptr(), out.stride(0)
+    if splitk_ws is None and impl == 6 and not torch.cuda.is_current_stream_capturing():
+        splitk_ws = splitk_workspace(out.device)
+    elif splitk_ws is None and impl == 6:
+        splitk_ws = _splitk_ws.get(out.device.index)        # during capture: only a buffer that already exists
+    if splitk_ws is not None:
+        d.splitk_ws, d.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
     if out_up is not None:
         d.out_up, d.out_up_y, d.out_up_x = out_up
     d.n_store = n_store
