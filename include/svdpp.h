@@ -42,6 +42,7 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   "splitk"     1: impl 6 splits the tiles of a short last wave along K when the descriptor carries splitk_ws; 0: never
  *                   ("splitk_min_kb": fewest 64-wide k-blocks a slice may get, default 4; "splitk_min_total_kb": only for
  *                   K / 64 >= this, default 64)
+ *   "r1_prefetch_max_kb"  the GEMM producer warp prefetches the residual tile into L2 for K / 64 <= this (default 5; 0: never)
  *   "pdl"        1: kernels are launched with programmatic stream serialisation (the prologue of kernel N+1
  *                   overlaps the tail of kernel N; every kernel waits on griddepcontrol before touching memory)
  * set returns 0, or -1 for an unknown key; get returns the value, or -1 for an unknown key.

@@ -46,6 +46,8 @@ Tuning& tuning() {
     v.splitk = (e != nullptr && e[0] != '0') ? 0 : 1;
     v.splitk_min_kb = 4;
     v.splitk_min_total_kb = 64;
+    e = getenv("SVDPP_NO_R1_PREFETCH");
+    v.r1_prefetch_max_kb = (e != nullptr && e[0] != '0') ? 0 : 5;
     e = getenv("SVDPP_EPI_DMA_MAX_KB");
     v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
     return v;
@@ -119,6 +121,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "epi_dma_max_kb") == 0) return &svdpp::tuning().epi_dma_max_kb;
   if (strcmp(key, "splitk") == 0) return &svdpp::tuning().splitk;
   if (strcmp(key, "splitk_min_kb") == 0) return &svdpp::tuning().splitk_min_kb;
+  if (strcmp(key, "r1_prefetch_max_kb") == 0) return &svdpp::tuning().r1_prefetch_max_kb;
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   return nullptr;
 }

@@ -50,6 +50,7 @@ struct Tuning {
   int epi_dma_max_kb;  // ... for K / 64 <= this
   int splitk;          // GEMM impl 6: split-K tail when the descriptor carries a workspace
   int splitk_min_kb;   // ... fewest k-blocks per slice
+  int r1_prefetch_max_kb;   // GEMM: producer warp prefetches the residual tile into L2 for K / 64 <= this (0: never)
   int splitk_min_total_kb;  // ... only for K / 64 >= this (the tail machinery costs ~20 us, a tile ~0.45 us per k-block)
 };
 Tuning& tuning();

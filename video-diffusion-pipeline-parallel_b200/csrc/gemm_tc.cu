@@ -1232,8 +1232,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   p.m_tiles = (d->M + 127) / 128;
   p.n_tiles = d->N / BN;
   {
-    static const bool no_prefetch = getenv("SVDPP_NO_R1_PREFETCH") != nullptr;
-    p.prefetch_r1 = (p.R1 != nullptr && !no_prefetch && d->K <= 640) ? 1 : 0;  // measured: K=320 +20 %, 640 +6 %, 1280 -3 %
+    // measured with the per-thread residual loads: K=320 +20 %, 640 +6 %, 1280 -3 %; with the residual on TMA loads the
+    // prefetch no longer pays at K = 640 (0.97x) and costs 1-5 % beyond, so it is kept for K <= 320 only
+    p.prefetch_r1 = (p.R1 != nullptr && p.num_kb <= tuning().r1_prefetch_max_kb) ? 1 : 0;
   }
 
   if (d->conv) {
