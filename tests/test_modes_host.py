@@ -85,3 +85,15 @@ def test_data_parallel_mode_prints_benchmark_json():
               "wall_clock_s", "per_sample_times_ms"):
         assert k in res, k
     assert res["mode"] == "data_parallel" and res["num_samples_measured"] == 4 and res["samples_per_rank"] == 2
+
+
+def test_tools_and_entry_points_compile():
+    # the measurement tools only run on the GPU box: at least keep them syntactically valid here
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"),
+                                                               os.path.join(root, "__graft_entry__.py")]
+    assert len(files) >= 15
+    for f in files:
+        py_compile.compile(f, doraise=True)
