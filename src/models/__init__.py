@@ -1,3 +1,7 @@
-from vdpp_b200.models import DummyUNet, StableVideoUNet  # noqa: F401
+"""``src.models`` — the reference's import path, served by the B200 package."""
+import vdpp_b200.models as _models
 
-__all__ = ["DummyUNet", "StableVideoUNet"]
+DummyUNet = _models.DummyUNet
+StableVideoUNet = _models.StableVideoUNet
+
+__all__ = ("DummyUNet", "StableVideoUNet")
