@@ -32,7 +32,8 @@ def _group_options(backend: str, rank: int, world_size: int, init_method: Option
     else:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if backend == "nccl" and torch.cuda.is_available():
-        local = int(os.environ.get("LOCAL_RANK", rank % max(torch.cuda.device_count(), 1)))
+        # the launcher's LOCAL_RANK, else whatever device the caller has already selected
+        local = int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else torch.cuda.current_device()
         opts["device_id"] = torch.device("cuda", local)
     return opts
 
