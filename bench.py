@@ -11,9 +11,18 @@ Stage placement for N>1 is --schedule ring by default (stage s of video v on ran
 PipelineStage.run_many_ring); the reference's fixed placement is timed as well and reported under
 "linear_pipeline".
 
+For N>1 the line also carries, for BOTH placements, the reference benchmark mode's own metrics (2 warm-up + 14
+measured videos, per-video completion times on the finishing rank: steady videos/min and first-video latency,
+reference src/modes/benchmark.py:256-267) and "multi_gpu_bit_equal": videos that went through the pipeline (incl.
+ones whose receive slot is a reused one) are recomputed on one GPU and must be torch.equal.
+At N=1 the line carries "library_baseline": the torch restatement of the same UNet with the same weights run with
+torch's library kernels (cuDNN / cuBLAS / SDPA, eager fp16) - BASELINE.md section 4.
+
 Reference arm:
   python bench.py --impl reference ...   times the CPU restatement of the reference's step (oracle/) on
-  the host cores on a bounded sample of the same workload.
+  the host cores on a bounded sample of the same workload (the reference's own SVD code cannot run here:
+  its UNet lives in diffusers, which is not installed; its own CPU simulator code IS timed, see
+  cpu_baseline.reference_simulator).
 """
 from __future__ import annotations
 
@@ -49,7 +58,9 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true",
                    help="enqueue every launch eagerly instead of replaying one CUDA graph per denoising step (within "
                         "+-1 %%: the host runs ~740 launches per step ahead of the GPU either way)")
+    p.add_argument("--force-graph", action="store_true", help="N=1: skip the eager-vs-graph measurement, use graphs")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-library-baseline", action="store_true")
     p.add_argument("--cpu-sample-frames", type=int, default=2)
     p.add_argument("--schedule", default="ring", choices=["ring", "linear"],
                    help="N>1: 'ring' rotates the stage->rank placement per video (no fill/drain bubble, no stage "
@@ -130,14 +141,38 @@ def reference_arm(args) -> None:
         "config": {"workload": f"SVD-XT {args.frames}f 576x1024 latent {H}x{W}, {args.denoise_steps} steps, no CFG",
                    "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "sec_per_sample_step": sec},
+                         "sec_per_sample_step": sec, "extrapolated": True,
+                         "extrapolation": f"x {args.frames}/{sf} frames x {args.denoise_steps} steps"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def cpu_dummy_simulator(total_steps: int = 25):
-    """The reference's CPU simulator workload (BASELINE config 1): DummyUNet(channels=4), latent [1,4,14,64,64]
-    fp32, `total_steps` steps on the host cores in one process (torch CPU kernels, as the reference runs it)."""
+    """The reference's CPU simulator workload (BASELINE config 1: DummyUNet(channels=4), latent [1,4,14,64,64] fp32) on
+    the host cores, run with the REFERENCE'S OWN PipelineStage + DummyUNet when an installed copy of the reference is
+    reachable (baseline/_ref or $VDPP_REFERENCE_ROOT; tools/reference_simulator.py), else with this repository's
+    mirror of those classes ("kind": "mirror").  25 steps x 1 rank, and 28 steps x 4 ranks over gloo (25 x 4 is
+    rejected by the reference's divisibility rule)."""
+    tool = os.path.join(ROOT, "tools", "reference_simulator.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT",
+                                                           "OMP_NUM_THREADS", "PYTHONPATH")}
+    runs = {}
+    for name, cmd in (
+            (f"{total_steps}x1", [sys.executable, tool, "--total-steps", str(total_steps), "--samples", "4", "--warmup", "2"]),
+            ("28x4", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4",
+                      "--master-addr", "127.0.0.1", "--master-port", "29688", tool, "--total-steps", "28",
+                      "--samples", "6", "--warmup", "2"])):
+        try:
+            r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("REFERENCE_SIMULATOR_JSON=")]
+            runs[name] = json.loads(line[-1].split("=", 1)[1]) if line else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # noqa: BLE001
+            runs[name] = {"error": f"{type(e).__name__}: {e}"}
+    first = runs.get(f"{total_steps}x1", {})
+    if "error" not in first:
+        return {"kind": "reference", "runs": runs, "ms_per_step": first["ms_per_step_per_rank"],
+                "videos_per_min": first["videos_per_min"], "cores": first["threads_per_rank"]}
+    # no reference tree: time this repository's mirror of the same classes in-process
     import torch
     from vdpp_b200.models import DummyUNet
     try:
@@ -154,9 +189,50 @@ def cpu_dummy_simulator(total_steps: int = 25):
         for step in range(total_steps):
             lat = model(lat, step)
         sec = time.perf_counter() - t0
-    return {"workload": f"DummyUNet(channels=4) latent 1x4x14x64x64 fp32, {total_steps} steps, 1 process",
+    return {"kind": "mirror", "why": first.get("error"),
+            "workload": f"DummyUNet(channels=4) latent 1x4x14x64x64 fp32, {total_steps} steps, 1 process",
             "ms_per_step": 1000.0 * sec / total_steps, "videos_per_min": 60.0 / sec, "cores": torch.get_num_threads(),
             "finite": bool(torch.isfinite(lat).all())}
+
+
+def library_baseline(model, dev, F_, H, W, T, guidance, seed):
+    """the torch restatement of the UNet (oracle/unet_torch.py) with the SAME weights, run by
+    torch's library kernels (cuDNN conv, cuBLASLt GEMM, SDPA attention, ATen norms) in eager fp16 behind the oracle's
+    restatement of the reference wrapper - 'the reference's own torch fp16 pipeline'.  A measured baseline beside the
+    native number; never on the product path."""
+    import torch
+    from oracle.svd_step import Conditioning, OracleStep
+    from oracle.unet_torch import UNetSpatioTemporalConditionModel
+    from vdpp_b200.models.svd_weights import random_state_dict
+    with torch.device("meta"):
+        lib = UNetSpatioTemporalConditionModel(norm_eps=model.unet.cfg["norm_eps"])
+    lib = lib.to_empty(device=dev).half().eval()
+    lib.load_state_dict(random_state_dict(None, seed=0, device=dev), strict=True)
+    cond = Conditioning(model._image_embeddings, model._image_latents, dtype=torch.float16, guidance_scale=guidance,
+                        num_frames=F_)
+    ostep = OracleStep(lib, T)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x0 = torch.randn((1, 4, F_, H, W), device=dev, generator=g, dtype=torch.float32).half() * model.init_noise_sigma
+    x = ostep(x0, 0, cond)                                    # warm-up (cuDNN / cuBLASLt heuristics)
+    native_1 = model(x0, 0)
+    n_steps = 3
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in range(n_steps):
+        x = ostep(x, s_ + 1, cond)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_steps
+    lib_1 = ostep(x0, 0, cond)
+    d = (native_1.float() - lib_1.float()).abs()
+    out = {"what": "torch eager fp16 (cuDNN/cuBLASLt/SDPA/ATen), same weights, same wrapper arithmetic",
+           "ms_per_step": ms, "videos_per_min": 60000.0 / (ms * T), "steps_timed": n_steps,
+           "first_step_max_abs_native_vs_library": d.max().item(), "latent_absmax": lib_1.float().abs().max().item(),
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+    del lib, ostep, cond
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -275,16 +351,47 @@ def main() -> None:
 
     ring = world > 1 and args.schedule == "ring"
 
-    def run_stream(n, supplier):
-        """Stream n videos; returns the latents that finished on this rank."""
-        if ring:
-            return [o for _, o in stage.run_many_ring(n, input_supplier=supplier)]
-        return stage.run_many(n, input_supplier=supplier if rank == 0 else None) or []
+    def run_stream(n, supplier, use_ring=None):
+        """Stream n videos; returns {video index: final latent} for the videos that finished on this rank."""
+        use_ring = ring if use_ring is None else use_ring
+        if use_ring:
+            return dict(stage.run_many_ring(n, input_supplier=supplier))
+        outs = stage.run_many(n, input_supplier=supplier if rank == 0 else None) or []
+        return dict(enumerate(outs))
+
+    def solo(x):
+        """All T steps of one video on this GPU alone (no pipeline): the bit-equality reference."""
+        for s_ in cfg.timesteps:
+            x = model(x, s_)
+        return x
 
     # ---- warm-up: first step eager, then one CUDA graph per step index is captured, then replays
     n_warm = Wm * world if ring else Wm
     warm_in = {i: t for i, t in zip(range(n_warm), make_inputs(n_warm, 1000))} if (ring or rank == 0) else {}
     run_stream(n_warm, lambda i: warm_in[i])
+    barrier()
+
+    # ---- N=1: eager enqueue vs one CUDA graph per step, measured here, the faster one is used for the timed regions
+    launch_mode = None
+    if world == 1 and not args.no_graph and not args.force_graph:
+        x = warm_in[0]
+        per_mode = {}
+        for mode in (False, True):
+            model.use_cuda_graph = mode
+            for s_ in range(min(T, 3)):            # captures the graphs of these steps on the first pass
+                model(x, s_)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(4):
+                for s_ in range(min(T, 3)):
+                    model(x, s_)
+            g1.record()
+            torch.cuda.synchronize()
+            per_mode["graph" if mode else "eager"] = g0.elapsed_time(g1) / (4 * min(T, 3))
+        model.use_cuda_graph = per_mode["graph"] <= per_mode["eager"]
+        launch_mode = {"step_ms_eager": per_mode["eager"], "step_ms_graph": per_mode["graph"],
+                       "chosen": "graph" if model.use_cuda_graph else "eager"}
     del warm_in
     barrier()
 
@@ -307,7 +414,26 @@ def main() -> None:
     launches = torch.tensor([native.LAUNCHES - launches0], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(launches)
-    finite = all(bool(torch.isfinite(o).all()) for o in outs)
+    finite = all(bool(torch.isfinite(o).all()) for o in outs.values())
+
+    # ---- N>1: a video that went through the pipeline must equal the same video computed on one GPU, bit for bit
+    # (NCCL handoffs, CUDA-graph replays, receive slots reused two hops later).  Every rank re-runs up to two of the
+    # videos that finished on it - in ring placement video v ends on rank (v + N - 1) % N, so videos of the first AND
+    # of later batches are covered; in fixed placement everything ends on the last rank.
+    bit_equal = None
+    if world > 1:
+        mine = sorted(outs)
+        picks = ([mine[0], mine[-1]] if len(mine) > 1 else mine)
+        ok = 1
+        for v in picks:
+            ref_in = inputs[v] if inputs is not None else make_inputs(v + 1, 0)[v]
+            ok &= int(torch.equal(solo(ref_in), outs[v]))
+        flag = torch.tensor([ok], device=dev)
+        n_checked = torch.tensor([len(picks)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(n_checked)
+        bit_equal = {"ring" if ring else "fixed": bool(flag.item()), "videos_checked": int(n_checked.item())}
+    del outs
 
     # ---- timed region 2: end to end through the public API with host buffers
     need_in = ring or rank == 0
@@ -345,20 +471,68 @@ def main() -> None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
 
-    # ---- N>1: the reference's fixed stage placement on the same stream, for comparison
-    linear_value = None
-    if ring:
-        n_lin = 2 * world
-        lin_in = make_inputs(n_lin, 500) if rank == 0 else None
-        barrier()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record()
-        stage.run_many(n_lin, input_supplier=(lambda i: lin_in[i]) if rank == 0 else None)
-        l1.record()
-        barrier()
-        lms = torch.tensor([l0.elapsed_time(l1)], device=dev)
-        dist.all_reduce(lms, op=dist.ReduceOp.MAX)
-        linear_value = n_lin / (float(lms.item()) / 1000.0) * 60.0
+    # ---- N>1: both placements measured the way the reference's benchmark mode does (src/modes/benchmark.py:229-267,
+    # SURVEY 8d cfg-3): 2 warm-up + 14 measured videos, completion times taken after a device synchronise on the rank a
+    # video finishes on; steady = measured videos / sum of their completion intervals; first-video time = pipeline fill.
+    placements = None
+    if world > 1:
+        n_warm_s, n_meas = 2, 14
+        placements = {}
+        for name in ("fixed", "ring"):
+            tot = n_warm_s + n_meas
+            if name == "ring":      # whole batches of `world` videos: completion times are per batch
+                tot = -(-tot // world) * world
+            s_in = make_inputs(tot, 2000) if (name == "ring" or rank == 0) else None
+            ends = []
+            barrier()
+            t_start = time.perf_counter()
+            if name == "fixed":
+                for i in range(tot):
+                    out_i = stage._process_single_latent(s_in[i] if rank == 0 else None, sample_idx=i)
+                    if last:
+                        torch.cuda.synchronize()
+                        ends.append(time.perf_counter())
+                        if i in (0, 2, tot - 1):          # slots 0 / 0 again (first reuse) / last: bit-equality below
+                            placements.setdefault("_keep", {})[i] = out_i.clone()
+            else:
+                for b in range(0, tot, world):
+                    stage.run_many_ring(world, input_supplier=lambda i, b=b: s_in[b + i])
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    ends.extend([time.perf_counter()] * world)
+            barrier()
+            if name == "fixed":
+                per = [e - (t_start if i == 0 else ends[i - 1]) for i, e in enumerate(ends)] if last else []
+            else:
+                per, prev = [], t_start
+                for b in range(0, tot, world):
+                    per.extend([(ends[b] - prev) / world] * world)
+                    prev = ends[b]
+            src_rank = world - 1 if name == "fixed" else 0
+            stats = torch.zeros(3, device=dev, dtype=torch.float64)
+            if rank == src_rank:
+                meas = per[n_warm_s:n_warm_s + n_meas] if name == "fixed" else per[world:]
+                first = per[0] if name == "fixed" else (ends[0] - t_start)
+                stats = torch.tensor([len(meas) / sum(meas) * 60.0, first, float(len(meas))], device=dev, dtype=torch.float64)
+            dist.broadcast(stats, src=src_rank)
+            placements[name] = {"steady_videos_per_min": float(stats[0]), "first_video_s": float(stats[1]),
+                                "videos_measured": int(stats[2]), "videos_warmup": n_warm_s if name == "fixed" else world}
+            if name == "fixed":
+                kept = placements.pop("_keep", {})
+                ok = 1
+                if last:
+                    again = make_inputs(tot, 2000)
+                    for i, o in kept.items():
+                        ok &= int(torch.equal(solo(again[i]), o))
+                    del again
+                flag = torch.tensor([ok], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                bit_equal["fixed" if ring else "fixed_steady_run"] = bool(flag.item())
+            del s_in
+        sizes = stage_sizes(T, world)
+        placements["ideal_efficiency_fixed"] = T / (world * max(sizes))
+        placements["method"] = ("reference src/modes/benchmark.py:229-267: completion times after a device synchronise, "
+                                "steady = measured / sum of intervals; ring placement completes a batch of N videos at once")
     bytes_lat = shape.numel() * 2
 
     if rank == 0:
@@ -387,9 +561,15 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_lat, "d2h_bytes_per_step": bytes_lat},
             "model_build_s": round(t_build, 1),
         }
-        if linear_value is not None:
-            result["linear_pipeline"] = {"value": linear_value, "unit": UNIT, "videos_timed": 2 * world,
-                                         "note": "reference placement (stage s on rank s), fill/drain included"}
+        if launch_mode is not None:
+            result["launch_mode"] = launch_mode
+        if placements is not None:
+            result["placements"] = placements
+            result["linear_pipeline"] = {"value": placements["fixed"]["steady_videos_per_min"], "unit": UNIT,
+                                         "note": "reference placement (stage s on rank s), steady; see placements"}
+        if bit_equal is not None:
+            result["multi_gpu_bit_equal"] = all(v for k, v in bit_equal.items() if k != "videos_checked")
+            result["multi_gpu_bit_equal_detail"] = bit_equal
     # ---- roofline of the dominant kernel (tcgen05 GEMM/conv family), instrumented eager pass, rank 0
     if rank == 0:
         model.use_cuda_graph = False
@@ -415,9 +595,12 @@ def main() -> None:
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of the same kernel family, from the committed ncu pass (profiles/)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")))
+            tname = next(n for n in ("r2_gemm_dram_traffic.json", "r1_gemm_dram_traffic.json")
+                         if os.path.exists(os.path.join(ROOT, "profiles", n)))
+            tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
             if F_ == 25 and (H, W) == (72, 128) and not args.guidance_scale:
-                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_gemm_dram_traffic.json (" + tj["source"] + ")"
+                traffic = tj["traffic_bytes_per_launch"]
+                traffic_src = f"profiles/{tname} ({tj['source']}; {tj.get('launches', '?')} launches then, {n_gemm} now)"
         except Exception:  # noqa: BLE001
             pass
         result["roofline"] = {
@@ -449,6 +632,14 @@ def main() -> None:
                 result["roofline_bandwidth"] = {"error": f"{type(e).__name__}: {e}"}
         result["whole_step_tflops"] = (fl["total"] / 1e12) / (ms_total / 1000.0 / (n_videos * T / world)) if world == 1 else None
 
+    # ---- GPU library baseline (torch eager fp16, same weights), rank 0 at N=1 only
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        try:
+            result["library_baseline"] = library_baseline(model, dev, F_, H, W, T, args.guidance_scale, args.seed)
+            result["library_baseline"]["native_speedup"] = result["library_baseline"]["ms_per_step"] / result["unet_step_ms"]
+        except Exception as e:  # noqa: BLE001
+            result["library_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- CPU baseline (oracle port on the host cores), rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -456,6 +647,7 @@ def main() -> None:
             v = videos_per_min_from_sample(sec, args.cpu_sample_frames, F_, T)
             result["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "extrapolated": True, "extrapolation": f"x {F_}/{args.cpu_sample_frames} frames x {T} steps",
                 "sample": f"1 denoising step of the oracle (torch fp32, CPU) at {args.cpu_sample_frames} of {F_} frames, "
                           f"full {H}x{W} latent, scaled by frames x {T} steps; {sec:.2f} s measured"}
             result["cpu_baseline"]["reference_simulator"] = cpu_dummy_simulator(T)

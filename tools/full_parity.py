@@ -44,7 +44,7 @@ def main(argv=None):
     with torch.device(dev):
         lib = UNetSpatioTemporalConditionModel().eval()        # default init from seed 0, on the GPU
     lib = lib.half()
-    nat = NativeUNet(lib.state_dict(), device=dev)
+    nat = NativeUNet(lib.state_dict(), config=lib.config, device=dev)
     ts = StableVideoUNet._default_timestep_schedule(T)
     model = StableVideoUNet(unet=nat, timesteps=ts).to(dev)
     torch.manual_seed(1)

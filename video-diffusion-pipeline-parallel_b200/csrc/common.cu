@@ -50,6 +50,8 @@ Tuning& tuning() {
     v.r1_prefetch_max_kb = (e != nullptr && e[0] != '0') ? 0 : 5;
     e = getenv("SVDPP_EPI_DMA_MAX_KB");
     v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
+    e = getenv("SVDPP_FMHA_STAGGER");
+    v.fmha_stagger = e != nullptr ? atoi(e) : 0;
     return v;
   }();
   return t;
@@ -123,6 +125,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "splitk_min_kb") == 0) return &svdpp::tuning().splitk_min_kb;
   if (strcmp(key, "r1_prefetch_max_kb") == 0) return &svdpp::tuning().r1_prefetch_max_kb;
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
+  if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
   return nullptr;
 }
 

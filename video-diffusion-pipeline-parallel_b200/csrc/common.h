@@ -52,6 +52,7 @@ struct Tuning {
   int splitk_min_kb;   // ... fewest k-blocks per slice
   int r1_prefetch_max_kb;   // GEMM: producer warp prefetches the residual tile into L2 for K / 64 <= this (0: never)
   int splitk_min_total_kb;  // ... only for K / 64 >= this (the tail machinery costs ~20 us, a tile ~0.45 us per k-block)
+  int fmha_stagger;         // two-tile FMHA: SM clocks by which query tile 1 starts behind tile 0 (0: together)
 };
 Tuning& tuning();
 

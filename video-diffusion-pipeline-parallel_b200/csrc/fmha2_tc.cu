@@ -29,6 +29,7 @@ struct Attn2Params {
   float scale_log2;
   __half* out;
   long long ldo;
+  int stagger;  // clocks by which query tile 1 starts behind tile 0 (softmax phases of the two warps of a scheduler interleave)
 };
 
 constexpr int A2_BQ = 128;                    // rows per query tile (two tiles per CTA)
@@ -88,7 +89,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // Measured dead end: evaluating every fourth (or eighth) exponential with a degree-3 polynomial on the FMA pipe
 // (poly3_exp2) to relieve the MUFU pipe was SLOWER (774 vs 799 TFLOP/s; with the packed-arithmetic loop 750 vs 805):
 // the softmax warps run out of issue slots before the MUFU pipe (73 % busy) saturates.
-template <int SPLIT>
+// QP = 1 (SPLIT == 1 only): quarter-pipelined softmax, see the softmax branch.  POLY = n > 0: one group of four
+// exponentials in every n is evaluated on the FMA pipe (poly3_exp2) instead of MUFU.
+template <int SPLIT, int QP, int POLY>
 __global__ void __launch_bounds__(A2Cfg<SPLIT>::THREADS, 1)
 attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const Attn2Params p) {
@@ -187,6 +190,14 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0, 43);
+      if (t == 1 && p.stagger > 0) {
+        // Phase offset between the two query tiles.  Warp w (tile 0) and warp w + 4 (tile 1) share a scheduler and its
+        // MUFU lanes; started together they stay in lock-step (both in the load / max / store phases at the same time,
+        // MUFU idle).  An offset, once there, persists: whoever is alone in its exp phase runs at full MUFU rate.
+        const long long c0 = clock64();
+        while (clock64() - c0 < p.stagger) {
+        }
+      }
       issue_s(0);
       for (int j = 0; j < p.n_kv; ++j) {
         const int s = j % A2_STAGES;
@@ -204,6 +215,164 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                       (j | k) != 0 ? 1u : 0u);
         umma_commit(&pv_done[t]);
         umma_commit(&v_empty[s]);
+      }
+    }
+  } else if constexpr (QP == 1) {
+    // ------------------------------------------------------------------ softmax, quarter-pipelined (SPLIT == 1)
+    // The 128 scores of a row are treated as four online-softmax blocks of 32 keys: the row maximum of quarter q + 1
+    // (FMNMX3, ALU pipe) has no dependence on the exponentials of quarter q (MUFU), so ptxas interleaves the two in one
+    // basic block and the max pass disappears from the critical path (it was a serial 64-deep chain, 15 % of the
+    // softmax warps' samples in ncu).  Each quarter's probabilities go to TMEM as soon as they are packed.
+    static_assert(SPLIT == 1, "quarter pipeline is written for one thread per row");
+    const int t = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_S = tmem_base + t * 128 + lane_sel;
+    const uint32_t tmem_O = tmem_base + 256 + t * 64 + lane_sel;
+    const uint32_t tmem_P = tmem_base + 384 + t * 64 + lane_sel;
+    const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
+    float m_used = -CUDART_INF_F;
+    float l_run = 0.f;
+    auto qmax = [](const uint32_t(&x)[32]) {
+      float a = fmax3(__uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]));
+      float b = fmax3(__uint_as_float(x[3]), __uint_as_float(x[4]), __uint_as_float(x[5]));
+      float c = fmax3(__uint_as_float(x[6]), __uint_as_float(x[7]), __uint_as_float(x[8]));
+      float d = fmax3(__uint_as_float(x[9]), __uint_as_float(x[10]), __uint_as_float(x[11]));
+      a = fmax3(a, __uint_as_float(x[12]), __uint_as_float(x[13]));
+      b = fmax3(b, __uint_as_float(x[14]), __uint_as_float(x[15]));
+      c = fmax3(c, __uint_as_float(x[16]), __uint_as_float(x[17]));
+      d = fmax3(d, __uint_as_float(x[18]), __uint_as_float(x[19]));
+      a = fmax3(a, __uint_as_float(x[20]), __uint_as_float(x[21]));
+      b = fmax3(b, __uint_as_float(x[22]), __uint_as_float(x[23]));
+      c = fmax3(c, __uint_as_float(x[24]), __uint_as_float(x[25]));
+      d = fmax3(d, __uint_as_float(x[26]), __uint_as_float(x[27]));
+      a = fmax3(a, __uint_as_float(x[28]), __uint_as_float(x[29]));
+      b = fmax3(b, __uint_as_float(x[30]), __uint_as_float(x[31]));
+      return fmaxf(fmaxf(a, b), fmaxf(c, d));
+    };
+    for (int j = 0; j < p.n_kv; ++j) {
+      const int valid = p.S - j * A2_BK;  // my columns [0, valid) of this block are real keys
+      mbar_wait(&s_full[t], j & 1, 49);
+      tc_fence_after();
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tmem_S + c * 32, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);  // the tensor core may overwrite S_t with block j+1 now
+      if (valid < A2_BK) {      // warp-uniform: only the last key block of an image can be partial
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) v[c][i] = 0xff800000u;  // -inf
+      }
+      float mq = qmax(v[0]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float m_blk = mq * p.scale_log2;
+        bool raise = false;
+        if (j == 0 && q == 0)
+          m_used = m_blk;
+        else
+          raise = m_blk > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, raise)) {
+          // rare: the reference maximum moves.  Everything accumulated under the old one is rescaled: O (every MMA that
+          // has touched it must have retired), the row sum, and the quarters of P(j) already stored for the pending PV.
+          if (j > 0) {
+            mbar_wait(&pv_done[t], (j - 1) & 1, 50);
+            tc_fence_after();
+          }
+          const float m_new = raise ? m_blk : m_used;
+          const float alpha = fast_exp2(m_used - m_new);
+          m_used = m_new;
+          l_run *= alpha;
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(tmem_O + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(tmem_O + c * 16, o);
+            }
+          }
+          if (q > 0) {
+            tmem_st_wait();
+            const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll 1
+            for (int c = 0; c < q; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(tmem_P + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&o[i]), a2);
+                o[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              tmem_st_x16(tmem_P + c * 16, o);
+            }
+          }
+          tmem_st_wait();
+        }
+        // the next quarter's maximum: independent of this quarter's exponentials, scheduled in between them
+        if (q < 3) mq = qmax(v[q + 1 < 4 ? q + 1 : 3]);
+        const float neg_m = -m_used;
+        const uint64_t negm2 = pack_f2(neg_m, neg_m);
+        uint64_t lsa = 0ull, lsb = 0ull;  // (0.f, 0.f)
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const uint64_t xa = ffma2(pack_f2(__uint_as_float(v[q][2 * i]), __uint_as_float(v[q][2 * i + 1])), scale2, negm2);
+          const uint64_t xb = ffma2(pack_f2(__uint_as_float(v[q][2 * i + 2]), __uint_as_float(v[q][2 * i + 3])), scale2, negm2);
+          float x0, x1, x2, x3;
+          unpack_f2(xa, x0, x1);
+          unpack_f2(xb, x2, x3);
+          float p0, p1, p2, p3;
+          if (POLY > 0 && (i / 2) % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) {
+            p0 = poly3_exp2(x0), p1 = poly3_exp2(x1), p2 = poly3_exp2(x2), p3 = poly3_exp2(x3);
+          } else {
+            p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+          }
+          lsa = fadd2(lsa, pack_f2(p0, p1));
+          lsb = fadd2(lsb, pack_f2(p2, p3));
+          pk[i] = pack_half2(p0, p1);
+          pk[i + 1] = pack_half2(p2, p3);
+        }
+        float a0, a1, b0, b1;
+        unpack_f2(lsa, a0, a1);
+        unpack_f2(lsb, b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
+        if (q == 0 && j > 0) {  // P_t(j-1) must have been consumed before its columns are rewritten
+          mbar_wait(&pv_done[t], (j - 1) & 1, 52);
+          tc_fence_after();
+        }
+        tmem_st_x16(tmem_P + q * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[t]);
+    }
+    mbar_wait(&pv_done[t], (p.n_kv - 1) & 1, 51);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + t * A2_BQ + r;
+    __half* dst = p.out + static_cast<long long>(row_base + q) * p.ldo + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tmem_O + c * 32, o);
+      tmem_ld_wait();
+      if (q < p.S) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          packed[i] = pack_half2(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) =
+              make_uint4(packed[4 * qd], packed[4 * qd + 1], packed[4 * qd + 2], packed[4 * qd + 3]);
       }
     }
   } else {
@@ -365,9 +534,9 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
-template <int SPLIT>
+template <int SPLIT, int QP, int POLY>
 static int launch_a2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Attn2Params& p, dim3 grid, cudaStream_t stream) {
-  auto kern = attn_spatial2_tc_kernel<SPLIT>;
+  auto kern = attn_spatial2_tc_kernel<SPLIT, QP, POLY>;
   static bool configured = false;
   if (!configured) {
     SVDPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
@@ -377,7 +546,9 @@ static int launch_a2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Attn
   return check_launch("attn_spatial2_tc_kernel");
 }
 
-int launch_attn_spatial2(const svdpp_attn_desc* d, int split, cudaStream_t stream) {
+// variant: 1 = thread per row, whole-row softmax (round 1); 2 = two threads per row; 4 = quarter-pipelined softmax;
+// 5 / 6 = quarter-pipelined with every 8th / 4th group of exponentials on the FMA pipe
+int launch_attn_spatial2(const svdpp_attn_desc* d, int variant, cudaStream_t stream) {
   SVDPP_CHECK_ARG(d->heads <= 65535 && d->n_img <= 65535, "attn: grid too large");
   Attn2Params p{};
   p.S = d->S;
@@ -388,6 +559,7 @@ int launch_attn_spatial2(const svdpp_attn_desc* d, int split, cudaStream_t strea
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
+  p.stagger = tuning().fmha_stagger;
   CUtensorMap tmQ, tmKV;
   const long long rows = static_cast<long long>(d->n_img) * d->S;
   uint64_t dims[2] = {static_cast<uint64_t>(d->ld), static_cast<uint64_t>(rows)};
@@ -397,8 +569,13 @@ int launch_attn_spatial2(const svdpp_attn_desc* d, int split, cudaStream_t strea
   if (encode_tmap_f16(&tmQ, d->qkv, 2, dims, str, box_q)) return -5;
   if (encode_tmap_f16(&tmKV, d->qkv, 2, dims, str, box_kv)) return -5;
   dim3 grid((d->S + 2 * A2_BQ - 1) / (2 * A2_BQ), d->heads, d->n_img);
-  if (split == 2) return launch_a2<2>(tmQ, tmKV, p, grid, stream);
-  return launch_a2<1>(tmQ, tmKV, p, grid, stream);
+  switch (variant) {
+    case 2: return launch_a2<2, 0, 0>(tmQ, tmKV, p, grid, stream);
+    case 4: return launch_a2<1, 1, 0>(tmQ, tmKV, p, grid, stream);
+    case 5: return launch_a2<1, 1, 8>(tmQ, tmKV, p, grid, stream);
+    case 6: return launch_a2<1, 1, 4>(tmQ, tmKV, p, grid, stream);
+    default: return launch_a2<1, 0, 0>(tmQ, tmKV, p, grid, stream);
+  }
 }
 
 }  // namespace svdpp

@@ -314,7 +314,7 @@ __global__ void attn_spatial_simt_kernel(const __half* qkv, long long ld, AttnPa
 }  // namespace svdpp
 
 namespace svdpp {
-int launch_attn_spatial2(const svdpp_attn_desc* d, int split, cudaStream_t stream);  // fmha2_tc.cu
+int launch_attn_spatial2(const svdpp_attn_desc* d, int variant, cudaStream_t stream);  // fmha2_tc.cu
 }
 
 using namespace svdpp;
@@ -334,7 +334,9 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
-  if (impl == 2 || impl == 3) return launch_attn_spatial2(d, impl == 3 ? 2 : 1, stream);
+  if (impl == 2) return launch_attn_spatial2(d, 1, stream);
+  if (impl == 3) return launch_attn_spatial2(d, 2, stream);
+  if (impl >= 4 && impl <= 6) return launch_attn_spatial2(d, impl, stream);
   if (impl == 1) {
     const long long total = static_cast<long long>(d->n_img) * d->heads * d->S;
     attn_spatial_simt_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(

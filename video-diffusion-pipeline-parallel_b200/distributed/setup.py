@@ -29,8 +29,12 @@ def _group_options(backend: str, rank: int, world_size: int, init_method: Option
                             "timeout": DEFAULT_TIMEOUT if timeout is None else timeout}
     if init_method:
         opts["init_method"] = init_method
-    else:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    elif "MASTER_ADDR" not in os.environ:
+        # loopback only when the job is known to live on one node; a multi-node launch without an address fails right
+        # away with torch's own error instead of waiting out the rendezvous timeout on 127.0.0.1
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world_size))
+        if local_world == world_size:
+            os.environ["MASTER_ADDR"] = "127.0.0.1"
     if backend == "nccl" and torch.cuda.is_available():
         # the launcher's LOCAL_RANK, else whatever device the caller has already selected
         local = int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else torch.cuda.current_device()

@@ -35,7 +35,11 @@ _HALF_BN = GEMM_BN // 2
 SVD_CONFIG = dict(in_channels=8, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
                   down_attn=(True, True, True, False), addition_time_embed_dim=256,
                   projection_class_embeddings_input_dim=768, layers_per_block=2, cross_attention_dim=1024,
-                  num_attention_heads=(5, 10, 20, 20), num_frames=25)
+                  num_attention_heads=(5, 10, 20, 20), num_frames=25,
+                  # GroupNorm eps per diffusers block class (kernel scalars).  The up blocks' value cannot be checked against
+                  # the diffusers source here: get_up_block does not forward the UNet's resnet_eps=1e-5 to the SpatioTemporal
+                  # up blocks, whose class default is 1e-6.  Override with config={"norm_eps": {"up": 1e-5}} if that is wrong.
+                  norm_eps=dict(down_attn=1e-6, down=1e-5, mid=1e-5, up=1e-6, transformer=1e-6, out=1e-5))
 
 
 def _ceil_to(x: int, m: int) -> int:
@@ -126,6 +130,7 @@ class NativeUNet(nn.Module):
         self.cfg = dict(SVD_CONFIG)
         if config:
             self.cfg.update(config)
+        self.cfg["norm_eps"] = {**SVD_CONFIG["norm_eps"], **((config or {}).get("norm_eps") or {})}
         self.device_ = torch.device(device)
         if self.device_.type != "cuda":
             raise NativeError("NativeUNet needs a CUDA device (there is no CPU path)")
@@ -248,7 +253,7 @@ class NativeUNet(nn.Module):
         return _Lin(self._keep(_pad_rows(w)), None, n)
 
     def _build_transformer(self, prefix: str, heads: int) -> dict:
-        P = dict(heads=heads)
+        P = dict(heads=heads, eps=self.cfg["norm_eps"]["transformer"])
         P["norm"], P["proj_in"] = self._norm(prefix + ".norm"), self._lin(prefix + ".proj_in")
         s, t = prefix + ".transformer_blocks.0", prefix + ".temporal_transformer_blocks.0"
         P["norm1"], P["qkv1"], P["out1"] = self._norm(s + ".norm1"), self._fuse_qkv(s + ".attn1"), self._lin(s + ".attn1.to_out.0")
@@ -279,7 +284,7 @@ class NativeUNet(nn.Module):
         self.down = []
         for i in range(len(boc)):
             blk = dict(res=[], attn=[], down=None)
-            eps = 1e-6 if attn[i] else 1e-5
+            eps = self.cfg["norm_eps"]["down_attn" if attn[i] else "down"]
             for j in range(L):
                 blk["res"].append(self._build_resblock(f"down_blocks.{i}.resnets.{j}", eps))
                 if attn[i]:
@@ -287,15 +292,15 @@ class NativeUNet(nn.Module):
             if i != len(boc) - 1:
                 blk["down"] = self._conv3x3(f"down_blocks.{i}.downsamplers.0.conv")
             self.down.append(blk)
-        self.mid = dict(res=[self._build_resblock("mid_block.resnets.0", 1e-5),
-                             self._build_resblock("mid_block.resnets.1", 1e-5)],
+        self.mid = dict(res=[self._build_resblock("mid_block.resnets.0", self.cfg["norm_eps"]["mid"]),
+                             self._build_resblock("mid_block.resnets.1", self.cfg["norm_eps"]["mid"])],
                         attn=self._build_transformer("mid_block.attentions.0", heads[-1]))
         self.up = []
         rheads, rattn = heads[::-1], attn[::-1]
         for i in range(len(boc)):
             blk = dict(res=[], attn=[], up=None)
             for j in range(L + 1):
-                blk["res"].append(self._build_resblock(f"up_blocks.{i}.resnets.{j}", 1e-5))
+                blk["res"].append(self._build_resblock(f"up_blocks.{i}.resnets.{j}", self.cfg["norm_eps"]["up"]))
                 if rattn[i]:
                     blk["attn"].append(self._build_transformer(f"up_blocks.{i}.attentions.{j}", rheads[i]))
             if i != len(boc) - 1:
@@ -425,7 +430,7 @@ class NativeUNet(nn.Module):
         C, heads = x.shape[1], P["heads"]
         scale = 1.0 / math.sqrt(C // heads)
         a = P["alpha"]
-        g = self._gn(x, P["norm"], n_img=n_img, HW=HW, eps=1e-6, silu=False)
+        g = self._gn(x, P["norm"], n_img=n_img, HW=HW, eps=P["eps"], silu=False)
         h0 = self._linear(g, P["proj_in"])
         # --- spatial block
         n1 = native.layernorm(self._new(M, C), h0, *P["norm1"])
@@ -529,7 +534,7 @@ class NativeUNet(nn.Module):
                     up = native.upsample2x(self._new(B * F * 4 * h * w, C), x, n_img=B * F, H=h, W=w, Cc=C)
                     h, w = 2 * h, 2 * w
                     x = self._conv(up, blk["up"], (B, F, h, w, C), TAPS_3X3)
-        a = self._gn(x, self.norm_out, n_img=B * F, HW=h * w, eps=1e-5)
+        a = self._gn(x, self.norm_out, n_img=B * F, HW=h * w, eps=self.cfg["norm_eps"]["out"])
         return self._conv(a, self.conv_out, (B, F, h, w, x.shape[1]), TAPS_3X3)
 
     @torch.no_grad()

@@ -177,6 +177,21 @@ class StableVideoUNet(nn.Module):
     def _cfg_on(self) -> bool:
         return self._guidance_scale is not None and self._guidance_scale > 1.0
 
+    def _check_conditioning_shapes(self, latent: torch.Tensor) -> None:
+        """The kernels index the conditioning tensors with the LATENT's shape (raw pointers, no length arguments), so a
+        mismatch would read out of bounds where the reference gets a torch broadcast / cat error (svd_unet.py:387,410)."""
+        B, C, F, H, W = latent.shape
+        if tuple(self._image_latents.shape) != (B, C, F, H, W):
+            raise ValueError(f"image_latents {tuple(self._image_latents.shape)} do not match the latent {tuple(latent.shape)}")
+        emb = self._image_embeddings
+        if emb.dim() != 3 or emb.shape[0] != B or emb.shape[1] != 1:
+            raise ValueError(f"image_embeddings must be [B={B}, 1, D] (one CLIP token per sample), got {tuple(emb.shape)}")
+        if self._added_time_ids.shape[0] != B:
+            raise ValueError(f"added_time_ids batch {self._added_time_ids.shape[0]} != latent batch {B}")
+        if self._cfg_on and self._guidance_scale_tensor.numel() != F:
+            raise ValueError(f"guidance ramp has {self._guidance_scale_tensor.numel()} frames (set_conditioning num_frames) "
+                             f"but the latent has {F}")
+
     # ------------------------------------------------------------------ one step
     def _step_native(self, latent: torch.Tensor, step: int) -> torch.Tensor:
         """pack -> NativeUNet (channels-last, CFG batched) -> CFG + Euler."""
@@ -256,6 +271,9 @@ class StableVideoUNet(nn.Module):
         if not latent.is_cuda:
             raise NativeError("StableVideoUNet.forward needs a CUDA latent: this build has no CPU path")
         latent = latent.to(torch.float16).contiguous()
+        if latent.dim() != 5:
+            raise ValueError(f"latent must be [B, C, F, H, W], got {tuple(latent.shape)}")
+        self._check_conditioning_shapes(latent)
         if not self.use_cuda_graph:
             return self._step(latent, step)
         key = (step, tuple(latent.shape))

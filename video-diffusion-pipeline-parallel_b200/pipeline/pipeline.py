@@ -102,12 +102,14 @@ class PipelineStage:
         return work, buf
 
     def _recv_latent(self) -> torch.Tensor:
-        """Blocking receive from ``rank-1`` (reference ``pipeline.py:75-80``)."""
+        """Blocking receive from ``rank-1`` (reference ``pipeline.py:75-80``).  The buffer is one of two persistent
+        slots, rewritten two receives later; a stage without steps would hand the slot itself on (the model returns a
+        fresh tensor per step otherwise), so it gets a copy - the reference allocates per receive."""
         self._log(f"waiting for latent from rank {self.config.rank - 1}")
         work, buf = self._post_recv()
         work.wait()
         self._log("received latent")
-        return buf
+        return buf if self.step_range.count else buf.clone()
 
     def _drain_send(self) -> None:
         if self._pending_send is not None:
@@ -211,7 +213,8 @@ class PipelineStage:
                         cur = self.model(cur, step)
                 if t == W - 1:
                     if exists:
-                        outputs.append((v, cur))
+                        # an empty last stage would append the receive slot itself (rewritten two hops later)
+                        outputs.append((v, cur if stages[t].count else cur.clone()))
                     break
                 # hop: my video goes to rank+1, the video of rank-1 comes to me (both at stage t -> t+1)
                 v_in = b * W + (r - 1 - t) % W
