@@ -572,13 +572,21 @@ def main() -> None:
             result["multi_gpu_bit_equal_detail"] = bit_equal
     # ---- roofline of the dominant kernel (tcgen05 GEMM/conv family), instrumented eager pass, rank 0
     if rank == 0:
-        model.use_cuda_graph = False
-        native.PROFILE = []
+        # per-kernel CUDA events need one ctypes launch per kernel: the Python orchestration of the same launch sequence
+        # (bit-identical to csrc/unet.cu's, tests/test_gpu_unet.py) with the same weights and conditioning
+        prof_model = StableVideoUNet.from_pretrained("random-init:0", timesteps=StableVideoUNet._default_timestep_schedule(T),
+                                                     device=dev, orchestrator="python")
+        prof_model.set_conditioning(model._image_embeddings, model._image_latents, guidance_scale=args.guidance_scale,
+                                    num_frames=F_)
         x = make_inputs(1, 0)[0]
+        prof_model(x, 0)                      # warm (frame-position cache, workspaces)
         torch.cuda.synchronize()
-        model(x, 0)
+        native.PROFILE = []
+        prof_model(x, 0)
         torch.cuda.synchronize()
         prof, native.PROFILE = native.PROFILE, None
+        del prof_model
+        torch.cuda.empty_cache()
         agg = {}
         for kind, flops, _shape, a, b in prof:
             d = agg.setdefault(kind, [0.0, 0.0, 0])

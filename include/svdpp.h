@@ -118,7 +118,15 @@ typedef struct svdpp_attn_desc {
   int32_t n_img, S, heads;
   float scale;                            /* 1/sqrt(64) */
 } svdpp_attn_desc;
+/* impl: 0 = one 128-query tile per CTA, two CTAs per SM (short sequences); 2 = two query tiles per CTA, P in tensor memory
+ * (round 1); 3 = 2 with two threads per row; 4 = 2 with the quarter-pipelined softmax (row maximum of the next 32 keys
+ * computed under the exponentials of the current 32); 5 / 6 = 4 with every 8th / 4th group of four exponentials evaluated
+ * as an FMA-pipe polynomial; 1 = plain CUDA-core kernel (bring-up cross-check).
+ * "fmha_stagger" (svdpp_set_tuning): SM clocks by which query tile 1 of impl 2..6 starts behind tile 0. */
 int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_stream stream);
+/* Debug: device buffer (>= 2 * ceil(S/128) * 8 uint32) that impl 2..6 fill with clock stamps of the softmax phases of two
+ * warps of their first CTA (tools/attn_trace.py); NULL switches it off.  No counterpart in the reference. */
+int svdpp_debug_attn_trace(void* dev_buffer);
 
 /* Temporal self-attention: for every (batch, pixel, head) a sequence of F <= 32 frames.
  * Token (b, f, p) is row (b*F + f)*HW + p.  Replaces attn1 of TemporalBasicTransformerBlock. */
@@ -210,6 +218,82 @@ int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, cons
                           const float* ln_g, const float* ln_b, float ln_eps, float tanh_scale, float* hidden_ws,
                           float* out, int32_t B, int32_t C, int32_t Ch, int32_t F, int32_t H, int32_t W,
                           svdpp_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole UNet operator, and one whole denoising step, behind a handle.
+ *
+ * Replaces, in one call each:
+ *   svdpp_unet_forward       unet(sample, timestep, encoder_hidden_states, added_time_ids, return_dict=False)[0]
+ *                            - diffusers UNetSpatioTemporalConditionModel.forward as the reference calls it at
+ *                            src/models/svd_unet.py:389-395,400-406,416-422 (boundary B2 of SURVEY section 8b)
+ *   svdpp_unet_forward_nhwc  the same with channels-last input / output (what the fused step uses internally)
+ *   svdpp_unet_step          StableVideoUNet.forward(latent, step), src/models/svd_unet.py:351-439: scale_model_input + cat +
+ *                            permute, the UNet (both classifier-free-guidance branches as one batch of 2), the guidance
+ *                            combine and the v-prediction Euler update
+ * The handle owns the packed weights (device memory allocated in svdpp_unet_load_weights, freed in svdpp_unet_destroy).
+ * Activations live in a caller-provided workspace of at least svdpp_unet_workspace_bytes(B, F, H, W) bytes (enough for
+ * batch B without and with guidance); its contents need not be preserved between calls.  The forward never allocates,
+ * never synchronises and is CUDA-graph capturable - except the FIRST call with a new frame count F, which computes and
+ * caches the frame-position embeddings (one cudaMalloc per transformer block): run one eager call per F first.
+ * One handle per device and host thread; not thread-safe.
+ * -------------------------------------------------------------------------------------------*/
+#define SVDPP_UNET_MAX_LEVELS 8
+typedef struct svdpp_unet svdpp_unet;          /* opaque */
+
+/* Architecture (diffusers unet/config.json) + GroupNorm eps per block class + kernel choices. */
+typedef struct svdpp_unet_config {
+  int32_t in_channels, out_channels;           /* 8, 4 */
+  int32_t n_levels;                            /* 4 */
+  int32_t block_out_channels[SVDPP_UNET_MAX_LEVELS];     /* 320, 640, 1280, 1280 */
+  int32_t down_attn[SVDPP_UNET_MAX_LEVELS];              /* 1, 1, 1, 0: CrossAttnDownBlockSpatioTemporal vs DownBlockSpatioTemporal */
+  int32_t num_attention_heads[SVDPP_UNET_MAX_LEVELS];    /* 5, 10, 20, 20 (head_dim 64) */
+  int32_t layers_per_block;                    /* 2 */
+  int32_t cross_attention_dim;                 /* 1024 */
+  int32_t addition_time_embed_dim;             /* 256 */
+  int32_t projection_class_embeddings_input_dim;  /* 768 */
+  float eps_down_attn, eps_down, eps_mid, eps_up, eps_transformer, eps_out;   /* 1e-6, 1e-5, 1e-5, 1e-6, 1e-6, 1e-5 */
+  int32_t gemm_impl;                           /* 3: choose the tile shape per GEMM (default); else force svdpp_gemm_f16's impl */
+  int32_t attn_impl;                           /* -1: by sequence length (default); else force svdpp_attn_spatial_f16's impl */
+  int32_t attn_impl_long;                      /* impl for S >= 1024 when attn_impl < 0 (0: library default) */
+} svdpp_unet_config;
+
+/* One entry of a diffusers-layout state_dict: `name` is the diffusers key ("down_blocks.0.resnets.0.spatial_res_block.
+ * conv1.weight", ...), `data` a contiguous DEVICE tensor; dtype 0 = fp16 (all weights), 1 = fp32 (accepted for the
+ * time_mixer.mix_factor scalars). */
+typedef struct svdpp_tensor_desc {
+  const char* name;
+  const void* data;
+  int32_t ndim;
+  int64_t shape[5];
+  int32_t dtype;
+} svdpp_tensor_desc;
+
+int svdpp_unet_create(svdpp_unet** out, const svdpp_unet_config* cfg);
+/* Repack the state_dict into kernel layouts (conv filters tap-major, q/k/v fused, GEGLU rows interleaved per tile, the
+ * up-sampling convs as four pre-summed 2x2-tap parity filters, every N padded to the tile width).  The caller's tensors
+ * are only read during the call (it synchronises the device once). */
+int svdpp_unet_load_weights(svdpp_unet* u, const svdpp_tensor_desc* tensors, int n);
+size_t svdpp_unet_weight_bytes(const svdpp_unet* u);
+/* 0 on error (svdpp_last_error) */
+size_t svdpp_unet_workspace_bytes(svdpp_unet* u, int B, int F, int H, int W);
+/* sample [B, F, in_channels, H, W] -> out [B, F, out_channels, H, W]; enc [B, 1, cross_attention_dim]; added_time_ids [B, 3] */
+int svdpp_unet_forward(svdpp_unet* u, const void* sample, float timestep, const void* enc, const void* added_time_ids,
+                       void* out, void* workspace, size_t workspace_bytes, int B, int F, int H, int W, svdpp_stream stream);
+/* x_in [B*F*H*W, in_channels] -> out [B*F*H*W, out_channels], both channels-last */
+int svdpp_unet_forward_nhwc(svdpp_unet* u, const void* x_in, float timestep, const void* enc, const void* added_time_ids,
+                            void* out, void* workspace, size_t workspace_bytes, int B, int F, int H, int W, svdpp_stream stream);
+/* One denoising step.  latent / image_latents / uncond_image_latents / out: [B, C, F, H, W] with C = out_channels.
+ * uncond_image_latents == NULL: no guidance, enc [B, 1, D], added_time_ids [B, 3].  Otherwise classifier-free guidance as
+ * one batch of 2B: enc [2B, 1, D] and added_time_ids [2B, 3] hold the unconditional half first, gs [F] is the per-frame
+ * guidance scale.  in_div = sqrt(sigma^2 + 1), c_v = -sigma / sqrt(sigma^2 + 1), c_x = sigma^2 + 1, dt = sigma_next - sigma
+ * are computed by the caller in fp32 (svdpp_euler_vpred_step has the formulas); timestep = 0.25 * ln(sigma). */
+int svdpp_unet_step(svdpp_unet* u, const void* latent, const void* image_latents, const void* uncond_image_latents,
+                    const void* enc, const void* added_time_ids, const void* gs, float timestep, float in_div, float c_v,
+                    float c_x, float sigma, float dt, void* out, void* workspace, size_t workspace_bytes, int B, int F, int H,
+                    int W, svdpp_stream stream);
+/* kernels launched by the last forward / step on this handle (bench.py's gpu_launches) */
+long long svdpp_unet_last_launches(const svdpp_unet* u);
+void svdpp_unet_destroy(svdpp_unet* u);
 
 #ifdef __cplusplus
 }

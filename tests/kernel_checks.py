@@ -362,8 +362,12 @@ def dummy_unet(C=4, Ch=16, step=7):
     torch.manual_seed(0)
     m = DummyUNet(channels=C, hidden_channels=Ch).to(DEV)
     x = torch.randn(1, C, 6, 16, 16, device=DEV)
+    m.native_cuda = False                     # the torch arithmetic of the reference's module
     with torch.no_grad():
         ref = m(x, step)
+        m.native_cuda = True                  # ... and the module's own dispatch to the native kernel
+        via_module = m(x, step)
+    assert (via_module - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-4
     hid = torch.empty(1, Ch, 6, 16, 16, device=DEV)
     out = native.dummy_unet_step(torch.empty_like(x), x, m.net[0].weight.contiguous(), m.net[0].bias,
                                  m.net[2].weight.contiguous(), m.net[2].bias, m.norm.weight, m.norm.bias, m.norm.eps,
@@ -579,19 +583,20 @@ ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
 
 
 # ------------------------------------------------------------------------------------------ whole UNet
-def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=None, seed=0):
+def _tiny_pair(cfg_over=None, gemm_impl=0, attn_impl=None, seed=0, orchestrator=None):
     from oracle.unet_torch import UNetSpatioTemporalConditionModel, tiny_config
     from vdpp_b200.models.native_unet import NativeUNet
     cfg = tiny_config(**(cfg_over or {}))
     torch.manual_seed(seed)
     oracle = UNetSpatioTemporalConditionModel(**cfg).to(DEV).half().eval()
-    nat = NativeUNet(oracle.state_dict(), config=oracle.config, device=DEV, gemm_impl=gemm_impl, attn_impl=attn_impl)
+    nat = NativeUNet(oracle.state_dict(), config=oracle.config, device=DEV, gemm_impl=gemm_impl, attn_impl=attn_impl,
+                     orchestrator=orchestrator)
     return oracle, nat
 
 
-def unet_tiny(gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, cfg_over=None):
+def unet_tiny(gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, cfg_over=None, orchestrator=None):
     """NativeUNet vs the torch oracle (fp16 library kernels) and vs the oracle in fp32, same weights."""
-    oracle, nat = _tiny_pair(cfg_over, gemm_impl, attn_impl)
+    oracle, nat = _tiny_pair(cfg_over, gemm_impl, attn_impl, orchestrator=orchestrator)
     g = torch.Generator(device=DEV)
     g.manual_seed(1)
     sample = torch.randn(B, Fr, 8, H, W, device=DEV, generator=g).half()
@@ -613,11 +618,12 @@ def unet_tiny(gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, cfg_over=None)
     return r
 
 
-def svd_steps(n_steps=4, total=25, cfg_scale=None, gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, graph=False):
+def svd_steps(n_steps=4, total=25, cfg_scale=None, gemm_impl=0, attn_impl=None, B=1, Fr=3, H=16, W=16, graph=False,
+              orchestrator=None):
     """StableVideoUNet (native) vs the oracle restatement of the reference wrapper, a few Euler steps."""
     from oracle.svd_step import OracleStep, dummy_conditioning
     from vdpp_b200.models import StableVideoUNet
-    oracle, nat = _tiny_pair(None, gemm_impl, attn_impl)
+    oracle, nat = _tiny_pair(None, gemm_impl, attn_impl, orchestrator=orchestrator)
     ts = StableVideoUNet._default_timestep_schedule(total)
     model = StableVideoUNet(unet=nat, timesteps=ts).to(DEV)
     model.use_cuda_graph = graph
@@ -659,6 +665,12 @@ UNET_CHECKS = {
     # the up blocks' GroupNorm eps at its other candidate value (UNVERIFIED U1 in oracle/unet_torch.py)
     "unet_tiny_tc_up_eps_1e5": lambda: unet_tiny(0, 0, cfg_over=dict(norm_eps={"up": 1e-5})),
     "unet_tiny_tc_fmha4": lambda: unet_tiny(0, 4),
+    # the same through the Python orchestration (ctypes launch per kernel); the default above is csrc/unet.cu
+    "unet_tiny_tc_pyorch": lambda: unet_tiny(0, 0, orchestrator="python"),
+    "unet_tiny_pair256_pyorch": lambda: unet_tiny(3, 0, orchestrator="python", cfg_over=dict(
+        block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))),
+    "svd_steps_tc_cfg_pyorch": lambda: svd_steps(cfg_scale=3.0, orchestrator="python"),
+    "svd_steps_tc_graph_pyorch": lambda: svd_steps(graph=True, orchestrator="python"),
 }
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
 UNET_CHECKS["unet_tiny_pair256_pdl"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], pdl=1)

@@ -55,6 +55,88 @@ def test_native_unet_is_deterministic_and_batch_independent():
     assert torch.equal(one[0], a[1])                               # per-sample statistics and attention
 
 
+PAIR256 = dict(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))
+
+
+@pytest.mark.parametrize("cfg_over,gemm_impl,shape", [(None, 0, (2, 3, 16, 16)), (PAIR256, 3, (1, 2, 16, 32)),
+                                                       (None, 2, (1, 3, 32, 16)), (dict(norm_eps={"up": 1e-5}), 0, (1, 3, 16, 16))])
+def test_c_orchestration_matches_python_orchestration_bit_for_bit(cfg_over, gemm_impl, shape):
+    """csrc/unet.cu (weight packing + launch sequence behind svdpp_unet_*) against models/native_unet.py's Python
+    orchestration of the same kernels: identical weights in, identical bits out - operator and wrapper step."""
+    from vdpp_b200.models import StableVideoUNet
+    B, Fr, H, W = shape
+    _, nat_c = kc._tiny_pair(cfg_over, gemm_impl, orchestrator="c")
+    _, nat_py = kc._tiny_pair(cfg_over, gemm_impl, orchestrator="python")
+    assert nat_c.orchestrator == "c" and nat_py.orchestrator == "python" and nat_c.weight_bytes() > 0
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sample = torch.randn(B, Fr, 8, H, W, device="cuda", generator=g).half()
+    enc = torch.randn(B, 1, 1024, device="cuda", generator=g).half()
+    ids = torch.tensor([[5.0, 127.0, 0.02]], device="cuda").half().repeat(B, 1)
+    for t in (1.6377, -0.75):
+        assert torch.equal(nat_c(sample, torch.tensor(t), enc, ids)[0], nat_py(sample, torch.tensor(t), enc, ids)[0])
+    dev = torch.device("cuda")
+    for gs in (None, 3.0):
+        outs = []
+        for nat in (nat_c, nat_py):
+            model = StableVideoUNet(unet=nat, timesteps=StableVideoUNet._default_timestep_schedule(25)).to(dev)
+            torch.manual_seed(5)
+            model.set_dummy_conditioning(B, Fr, H, W, dev, guidance_scale=gs)
+            torch.manual_seed(6)
+            x = torch.randn(B, 4, Fr, H, W, device=dev).half() * model.init_noise_sigma
+            for s in range(3):
+                x = model(x, s)
+            outs.append(x)
+        assert torch.equal(outs[0], outs[1])
+
+
+def test_unet_c_abi_five_calls():
+    """one forward of the UNet operator with nothing but svdpp_unet_create / _load_weights /
+    _workspace_bytes / _forward / _destroy (torch only provides device memory), against the Python orchestration."""
+    import ctypes as C
+    from vdpp_b200 import native
+    oracle, nat_py = kc._tiny_pair(orchestrator="python")
+    lib = native.load()
+    cfg = native.UNetConfig()
+    boc, heads, attn = oracle.config["block_out_channels"], oracle.config["num_attention_heads"], oracle.config["down_attn"]
+    cfg.in_channels, cfg.out_channels, cfg.n_levels = 8, 4, len(boc)
+    for i in range(len(boc)):
+        cfg.block_out_channels[i], cfg.num_attention_heads[i], cfg.down_attn[i] = boc[i], heads[i], int(attn[i])
+    cfg.layers_per_block, cfg.cross_attention_dim = 2, 1024
+    cfg.addition_time_embed_dim, cfg.projection_class_embeddings_input_dim = 256, 768
+    cfg.eps_down_attn, cfg.eps_down, cfg.eps_mid, cfg.eps_up, cfg.eps_transformer, cfg.eps_out = 1e-6, 1e-5, 1e-5, 1e-6, 1e-6, 1e-5
+    cfg.gemm_impl, cfg.attn_impl, cfg.attn_impl_long = 0, -1, 0
+    h = C.c_void_p()
+    assert lib.svdpp_unet_create(C.byref(h), C.byref(cfg)) == 0, lib.svdpp_last_error()
+    sd = {k: v.detach().half().contiguous() for k, v in oracle.state_dict().items()}
+    descs = (native.TensorDesc * len(sd))()
+    for i, (k, v) in enumerate(sd.items()):
+        descs[i].name, descs[i].data, descs[i].ndim, descs[i].dtype = k.encode(), v.data_ptr(), v.dim(), 0
+        for j, d in enumerate(v.shape):
+            descs[i].shape[j] = d
+    assert lib.svdpp_unet_load_weights(h, descs, len(sd)) == 0, lib.svdpp_last_error()
+    B, Fr, H, W = 2, 3, 16, 16
+    need = lib.svdpp_unet_workspace_bytes(h, B, Fr, H, W)
+    assert need > 0, lib.svdpp_last_error()
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    sample = torch.randn(B, Fr, 8, H, W, device="cuda", generator=g).half()
+    enc = torch.randn(B, 1, 1024, device="cuda", generator=g).half()
+    ids = torch.tensor([[5.0, 127.0, 0.02]], device="cuda").half().repeat(B, 1)
+    out = torch.full((B, Fr, 4, H, W), float("nan"), device="cuda", dtype=torch.float16)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):          # second call: frame-position cache hit, workspace reused as is
+        rc = lib.svdpp_unet_forward(h, sample.data_ptr(), 0.5, enc.data_ptr(), ids.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                    need, B, Fr, H, W, stream)
+        assert rc == 0, lib.svdpp_last_error()
+    torch.cuda.synchronize()
+    assert lib.svdpp_unet_last_launches(h) > 100
+    assert torch.equal(out, nat_py(sample, torch.tensor(0.5), enc, ids)[0])
+    # a workspace that is too small is an error, not an overrun
+    assert lib.svdpp_unet_forward(h, sample.data_ptr(), 0.5, enc.data_ptr(), ids.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                  need // 8, B, Fr, H, W, stream) != 0
+    lib.svdpp_unet_destroy(h)
+
+
 def test_full_size_step_properties():
     """BASELINE config 3 shape (25 frames, 72x128 latent), random-init 1.5 B-parameter UNet:
     finite output, determinism across CUDA-graph replay vs eager, Euler contraction of the noise scale."""
@@ -74,6 +156,16 @@ def test_full_size_step_properties():
     model(x, 0)
     replay = model(x, 0)
     assert torch.equal(replay, eager)
+    # the full-size step through the Python orchestration of the same kernels: same bits
+    from vdpp_b200.models.native_unet import NativeUNet
+    from vdpp_b200.models.svd_weights import random_state_dict
+    assert model.unet.orchestrator == "c"
+    py = StableVideoUNet(unet=NativeUNet(random_state_dict(None, seed=0, device=dev), device=dev, orchestrator="python"),
+                         timesteps=StableVideoUNet._default_timestep_schedule(25)).to(dev)
+    py.set_conditioning(model._image_embeddings, model._image_latents, num_frames=25)
+    assert torch.equal(py(x, 0), eager)
+    del py
+    torch.cuda.empty_cache()
 
 
 def test_safetensors_checkpoint_roundtrip(tmp_path):
@@ -142,12 +234,12 @@ def test_north_star_tolerance_config4_25_frames_cfg():
 def test_norm_eps_table_reaches_the_kernels():
     """GroupNorm eps is a per-block-class entry of the UNet config (down_attn / down / mid / up / transformer / out),
     shared by the oracle and NativeUNet; the up blocks' value is the one UNVERIFIED choice with two candidates."""
-    oracle, nat = kc._tiny_pair()
+    oracle, nat = kc._tiny_pair(orchestrator="python")
     assert oracle.config["norm_eps"]["up"] == 1e-6 and nat.cfg["norm_eps"] == oracle.config["norm_eps"]
     assert all(r["eps"] == 1e-6 for blk in nat.up for r in blk["res"])
     assert all(r["eps"] == 1e-5 for r in nat.mid["res"]) and nat.down[-1]["res"][0]["eps"] == 1e-5
     assert nat.down[0]["res"][0]["eps"] == 1e-6 and nat.down[0]["attn"][0]["eps"] == 1e-6
-    oracle5, nat5 = kc._tiny_pair(dict(norm_eps={"up": 1e-5}))
+    oracle5, nat5 = kc._tiny_pair(dict(norm_eps={"up": 1e-5}), orchestrator="python")
     assert oracle5.up_blocks[0].resnets[0].spatial_res_block.norm1.eps == 1e-5
     assert all(r["eps"] == 1e-5 for blk in nat5.up for r in blk["res"])
 

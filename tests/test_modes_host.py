@@ -87,6 +87,35 @@ def test_data_parallel_mode_prints_benchmark_json():
     assert res["mode"] == "data_parallel" and res["num_samples_measured"] == 4 and res["samples_per_rank"] == 2
 
 
+def test_production_flags_match_reference():
+    from vdpp_b200.modes.production import build_parser
+    # reference src/modes/production.py:20-47: --total-steps is required, everything else has these defaults
+    with pytest.raises(SystemExit):
+        build_parser().parse_args([])
+    a = build_parser().parse_args(["--total-steps", "25", "--latent-shape", "1", "4", "25", "72", "128"])
+    assert (a.num_samples, a.seed, a.backend, a.fps, a.motion_bucket_id) == (1, 0, "auto", 6, 127)
+    assert a.model_id == "stabilityai/stable-video-diffusion-img2vid-xt" and a.latent_shape == [1, 4, 25, 72, 128]
+    assert not a.enable_memory_opt and not a.attention_slicing and a.timesteps is None
+    import src.modes.production as shim                      # the reference's import path resolves
+    assert shim.main is not None
+
+
+def test_comparison_sweep_writes_reference_csv(tmp_path):
+    """The pipeline-vs-data-parallel sweep of reference scripts/benchmark_comparison.sh, on CPU/gloo with the dummy model."""
+    import csv
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import benchmark_comparison as bc
+    path, rows = bc.main(["--gpu-counts", "1,2", "--device", "cpu", "--total-steps", "4", "--num-samples", "2",
+                          "--warmup-samples", "1", "--latent-frames", "2", "--latent-height", "8", "--latent-width", "8",
+                          "--hidden-channels", "8", "--results-dir", str(tmp_path)])
+    table = list(csv.reader(open(path)))
+    assert table[0] == ["mode", "gpu_count", "total_steps", "steps_per_gpu", "num_samples", "first_sample_s",
+                        "avg_sample_s", "throughput_sps"]                     # benchmark_comparison.sh:47
+    assert [(r[0], r[1]) for r in table[1:]] == [("pipeline_parallel", "1"), ("data_parallel", "1"),
+                                                 ("pipeline_parallel", "2"), ("data_parallel", "2")]
+    assert all(float(r[7]) > 0 for r in table[1:])
+
+
 def test_tools_and_entry_points_compile():
     # the measurement tools only run on the GPU box: at least keep them syntactically valid here
     import glob

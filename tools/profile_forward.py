@@ -26,10 +26,13 @@ def main():
     ap.add_argument("--once", action="store_true", help="a single eager step and exit (for ncu)")
     ap.add_argument("--library", action="store_true", help="also time the torch oracle in fp16 on the GPU")
     ap.add_argument("--guidance-scale", type=float, default=None)
+    ap.add_argument("--orchestrator", default="python", choices=["python", "c"],
+                    help="per-launch CUDA events need the Python orchestration (one ctypes call per kernel); the C "
+                         "orchestration (csrc/unet.cu, the product default) is timed per step beside it")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     F_, H, W = a.frames, a.height, a.width
-    model = StableVideoUNet.from_pretrained("random-init:0", device=dev)
+    model = StableVideoUNet.from_pretrained("random-init:0", device=dev, orchestrator=a.orchestrator)
     torch.manual_seed(1)
     model.set_dummy_conditioning(1, F_, H, W, dev, guidance_scale=a.guidance_scale)
     x = torch.randn(1, 4, F_, H, W, device=dev).half() * model.init_noise_sigma
@@ -38,7 +41,27 @@ def main():
     if a.once:
         print("finite", bool(torch.isfinite(out).all()), "absmax", out.float().abs().max().item())
         return
-    res = {"frames": F_, "latent": [H, W], "finite": bool(torch.isfinite(out).all())}
+    res = {"frames": F_, "latent": [H, W], "finite": bool(torch.isfinite(out).all()), "orchestrator": a.orchestrator}
+    if a.orchestrator == "python":      # the product path (one svdpp_unet_step call per step), eager and graph
+        cm = StableVideoUNet.from_pretrained("random-init:0", device=dev, orchestrator="c")
+        cm.set_conditioning(model._image_embeddings, model._image_latents, guidance_scale=a.guidance_scale, num_frames=F_)
+        res["c_equals_python"] = bool(torch.equal(cm(x, 0), out))
+        for mode in ("eager", "graph"):
+            cm.use_cuda_graph = mode == "graph"
+            for _ in range(3):
+                cm(x, 1)
+            torch.cuda.synchronize()
+            tt = []
+            for _ in range(5):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                cm(x, 1)
+                c1.record()
+                torch.cuda.synchronize()
+                tt.append(c0.elapsed_time(c1))
+            res[f"c_{mode}_step_ms"] = min(tt)
+        del cm
+        torch.cuda.empty_cache()
     # eager timing
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []

@@ -30,7 +30,9 @@ struct Attn2Params {
   __half* out;
   long long ldo;
   int stagger;  // clocks by which query tile 1 starts behind tile 0 (softmax phases of the two warps of a scheduler interleave)
+  unsigned int* trace;  // debug: phase timestamps of softmax warps 0 and 4 of CTA (0,0,0), [2][n_kv][8] (NULL: off)
 };
+static unsigned int* g_attn_trace = nullptr;
 
 constexpr int A2_BQ = 128;                    // rows per query tile (two tiles per CTA)
 constexpr int A2_BK = 128;                    // keys per block
@@ -149,6 +151,13 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
+  const bool trace_on = p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 &&
+                        warp < Cfg::SM_WARPS && (warp & 3) == 0 && (SPLIT == 1 || (warp >> 2 & 1) == 0);
+  unsigned int* const trace = trace_on ? p.trace + (warp / (4 * SPLIT)) * (p.n_kv * 8) : nullptr;
+#define SVDPP_TR(j, ev)                                          \
+  do {                                                           \
+    if (trace_on) trace[(j) * 8 + (ev)] = static_cast<unsigned int>(clock64()); \
+  } while (0)
 
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
@@ -252,14 +261,17 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     };
     for (int j = 0; j < p.n_kv; ++j) {
       const int valid = p.S - j * A2_BK;  // my columns [0, valid) of this block are real keys
+      SVDPP_TR(j, 0);
       mbar_wait(&s_full[t], j & 1, 49);
       tc_fence_after();
+      SVDPP_TR(j, 1);
       uint32_t v[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_x32(tmem_S + c * 32, v[c]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // the tensor core may overwrite S_t with block j+1 now
+      SVDPP_TR(j, 2);
       if (valid < A2_BK) {      // warp-uniform: only the last key block of an image can be partial
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -268,6 +280,9 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (c * 32 + i >= valid) v[c][i] = 0xff800000u;  // -inf
       }
       float mq = qmax(v[0]);
+      uint32_t pk[4][16];
+      constexpr int FIRST_ST = 2;  // P(j) is first stored after this quarter: PV(j-1), issued at the end of block j-1,
+                                   // has long retired by then (waiting for it after quarter 0 stalled the warp)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float m_blk = mq * p.scale_log2;
@@ -298,30 +313,40 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               tmem_st_x16(tmem_O + c * 16, o);
             }
           }
-          if (q > 0) {
-            tmem_st_wait();
+          if (q > 0) {  // quarters of P(j) computed under the old maximum: in registers up to FIRST_ST, in TMEM after
             const __half2 a2 = __float2half2_rn(alpha);
-#pragma unroll 1
-            for (int c = 0; c < q; ++c) {
-              uint32_t o[16];
-              tmem_ld_x16(tmem_P + c * 16, o);
-              tmem_ld_wait();
+            if (q <= FIRST_ST) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&o[i]), a2);
-                o[i] = *reinterpret_cast<uint32_t*>(&h);
+              for (int c = 0; c < q; ++c)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  __half2 h = __hmul2(*reinterpret_cast<__half2*>(&pk[c][i]), a2);
+                  pk[c][i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            } else {
+              tmem_st_wait();
+#pragma unroll 1
+              for (int c = 0; c < q; ++c) {
+                uint32_t o[16];
+                tmem_ld_x16(tmem_P + c * 16, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  __half2 h = __hmul2(*reinterpret_cast<__half2*>(&o[i]), a2);
+                  o[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                tmem_st_x16(tmem_P + c * 16, o);
               }
-              tmem_st_x16(tmem_P + c * 16, o);
             }
           }
           tmem_st_wait();
         }
+        if (q == 0) SVDPP_TR(j, 3);
         // the next quarter's maximum: independent of this quarter's exponentials, scheduled in between them
         if (q < 3) mq = qmax(v[q + 1 < 4 ? q + 1 : 3]);
         const float neg_m = -m_used;
         const uint64_t negm2 = pack_f2(neg_m, neg_m);
         uint64_t lsa = 0ull, lsb = 0ull;  // (0.f, 0.f)
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const uint64_t xa = ffma2(pack_f2(__uint_as_float(v[q][2 * i]), __uint_as_float(v[q][2 * i + 1])), scale2, negm2);
@@ -337,22 +362,31 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           }
           lsa = fadd2(lsa, pack_f2(p0, p1));
           lsb = fadd2(lsb, pack_f2(p2, p3));
-          pk[i] = pack_half2(p0, p1);
-          pk[i + 1] = pack_half2(p2, p3);
+          pk[q][i] = pack_half2(p0, p1);
+          pk[q][i + 1] = pack_half2(p2, p3);
         }
         float a0, a1, b0, b1;
         unpack_f2(lsa, a0, a1);
         unpack_f2(lsb, b0, b1);
         l_run += (a0 + a1) + (b0 + b1);
-        if (q == 0 && j > 0) {  // P_t(j-1) must have been consumed before its columns are rewritten
-          mbar_wait(&pv_done[t], (j - 1) & 1, 52);
-          tc_fence_after();
+        if (q == 0) SVDPP_TR(j, 4);
+        if (q == FIRST_ST) {
+          if (j > 0) {  // P_t(j-1) must have been consumed before its columns are rewritten
+            mbar_wait(&pv_done[t], (j - 1) & 1, 52);
+            tc_fence_after();
+          }
+          SVDPP_TR(j, 5);
+#pragma unroll
+          for (int c = 0; c <= FIRST_ST; ++c) tmem_st_x16(tmem_P + c * 16, pk[c]);
+        } else if (q > FIRST_ST) {
+          tmem_st_x16(tmem_P + q * 16, pk[q]);
         }
-        tmem_st_x16(tmem_P + q * 16, pk);
       }
+      SVDPP_TR(j, 6);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[t]);
+      SVDPP_TR(j, 7);
     }
     mbar_wait(&pv_done[t], (p.n_kv - 1) & 1, 51);
     tc_fence_after();
@@ -390,8 +424,10 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     float l_run = 0.f;
     for (int j = 0; j < p.n_kv; ++j) {
       const int valid = p.S - j * A2_BK - hf * COLS;  // my columns [0, valid) of this block are real keys
+      SVDPP_TR(j, 0);
       mbar_wait(&s_full[t], j & 1, 49);
       tc_fence_after();
+      SVDPP_TR(j, 1);
       uint32_t v[COLS];
       {
         uint32_t(*v4)[32] = reinterpret_cast<uint32_t(*)[32]>(v);
@@ -401,6 +437,7 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // the tensor core may overwrite S_t with block j+1 now
+      SVDPP_TR(j, 2);
       if (valid < COLS) {  // warp-uniform: only the last key block of an image can be partial
 #pragma unroll
         for (int i = 0; i < COLS; ++i)
@@ -441,6 +478,7 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tmem_st_wait();
       }
       // probabilities -> packed fp16 -> this tile's P columns
+      SVDPP_TR(j, 3);
       const float neg_m = -m_used;
       uint32_t pk[COLS / 2];
       if constexpr (SPLIT == 1) {
@@ -484,18 +522,22 @@ attn_spatial2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         l_run += (ls0 + ls1) + (ls2 + ls3);
       }
+      SVDPP_TR(j, 4);
       if (j > 0) {  // P_t(j-1) must have been consumed (long since: it was issued a whole exp phase ago)
         mbar_wait(&pv_done[t], (j - 1) & 1, 52);
         tc_fence_after();
       }
+      SVDPP_TR(j, 5);
       {
         const uint32_t(*pk2)[32] = reinterpret_cast<const uint32_t(*)[32]>(pk);
 #pragma unroll
         for (int c = 0; c < COLS / 64; ++c) tmem_st_x32(tmem_P + c * 32, pk2[c]);
+        SVDPP_TR(j, 6);
         tmem_st_wait();
       }
       tc_fence_before();
       mbar_arrive(&p_ready[t]);
+      SVDPP_TR(j, 7);
     }
     mbar_wait(&pv_done[t], (p.n_kv - 1) & 1, 51);
     tc_fence_after();
@@ -560,6 +602,7 @@ int launch_attn_spatial2(const svdpp_attn_desc* d, int variant, cudaStream_t str
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
   p.stagger = tuning().fmha_stagger;
+  p.trace = g_attn_trace;
   CUtensorMap tmQ, tmKV;
   const long long rows = static_cast<long long>(d->n_img) * d->S;
   uint64_t dims[2] = {static_cast<uint64_t>(d->ld), static_cast<uint64_t>(rows)};
@@ -579,3 +622,10 @@ int launch_attn_spatial2(const svdpp_attn_desc* d, int variant, cudaStream_t str
 }
 
 }  // namespace svdpp
+
+// Debug hook (tools/attn_trace.py): device buffer of >= 2 * n_kv * 8 uint32 that the two-tile FMHA fills with clock
+// stamps of the softmax phases of warps 0 and 4 of its first CTA; NULL switches the tracing off again.
+extern "C" int svdpp_debug_attn_trace(void* dev_buffer) {
+  svdpp::g_attn_trace = static_cast<unsigned int*>(dev_buffer);
+  return 0;
+}

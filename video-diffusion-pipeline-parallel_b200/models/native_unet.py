@@ -15,8 +15,13 @@ Activations are channels-last matrices [M = B*F*H*W, C] end to end: the spatial 
 transformer *is* the conv layout, so the reference's permutes/reshapes disappear; the temporal branch
 is reached by index arithmetic (frame stride H*W rows) instead of a transposed copy.
 
-This module only orchestrates: all arithmetic on activations is in ``libsvdpp.so`` (``native.py``).
-torch is used for allocation, one-time weight repacking and CUDA streams.  There is no CPU path.
+Two orchestrations of the same launch sequence exist and must agree bit for bit (tests/test_gpu_unet.py):
+  * ``orchestrator="c"`` (default): the class is a thin caller of the ``svdpp_unet_*`` handle of ``include/svdpp.h`` -
+    weight packing, the ~740 launches of a forward, the activation arena and the whole denoising step
+    (``svdpp_unet_step``) live in ``csrc/unet.cu``; Python passes pointers and a workspace tensor;
+  * ``orchestrator="python"``: this module packs the weights with torch and issues every launch through ctypes
+    (``native.py``) - kept for per-kernel timing (``native.PROFILE``) and as the cross-check of the C orchestration.
+All arithmetic on activations is in ``libsvdpp.so`` either way.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -125,7 +130,8 @@ def window_path_ok(W: int, C: int) -> bool:
 class NativeUNet(nn.Module):
     def __init__(self, state_dict: Mapping[str, torch.Tensor], config: Optional[dict] = None,
                  device: torch.device | str = "cuda", gemm_impl: Optional[int] = None,
-                 attn_impl: Optional[int] = None):
+                 attn_impl: Optional[int] = None, orchestrator: Optional[str] = None,
+                 attn_impl_long: Optional[int] = None):
         super().__init__()
         self.cfg = dict(SVD_CONFIG)
         if config:
@@ -141,15 +147,55 @@ class NativeUNet(nn.Module):
         # None: the two-tile FMHA (impl 2, P in TMEM) for long sequences, where its one CTA per SM amortises the
         # prologue, and the 2-CTAs-per-SM kernel (impl 0) for S < 1024; an int forces one kernel (1 = CUDA cores)
         self.attn_impl = attn_impl
+        # spatial FMHA kernel for S >= 1024 (svdpp_attn_spatial_f16's impl): 4 = two query tiles per CTA with the
+        # quarter-pipelined softmax (A/B in profiles/r2_*), 2 = the round-1 kernel
+        self.attn_impl_long = int(os.environ.get("SVDPP_ATTN_IMPL_LONG", "4")) if attn_impl_long is None else attn_impl_long
+        self.orchestrator = (orchestrator or os.environ.get("SVDPP_ORCHESTRATOR", "c")).lower()
+        if self.orchestrator not in ("c", "python"):
+            raise ValueError("orchestrator must be 'c' or 'python'")
         self.dtype = torch.float16
         self._sd = state_dict
         self._tensors: List[torch.Tensor] = []   # keeps packed weights alive / counted
         self._pos_cache: Dict[Tuple[str, int], torch.Tensor] = {}
         self._gn_ws: Optional[torch.Tensor] = None
         self._sms: Optional[int] = None
-        native.splitk_workspace(self.device_)    # scratch of the split-K tail (256x320 tiles, long K): before any graph capture
-        self._build()
+        self._handle: Optional[native.UNetHandle] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_shape = None
+        if self.orchestrator == "c":
+            with torch.cuda.device(self.device_):
+                sd = {k: v.detach().to(self.device_) for k, v in state_dict.items()}
+                self._handle = native.UNetHandle(self.cfg, sd, gemm_impl=self.gemm_impl, attn_impl=self.attn_impl,
+                                                 attn_impl_long=self.attn_impl_long)
+                del sd
+        else:
+            native.splitk_workspace(self.device_)    # scratch of the split-K tail: before any graph capture
+            self._build()
         self._sd = None
+
+    # ------------------------------------------------------------------ C orchestration (svdpp_unet_*)
+    def _workspace(self, B: int, F: int, H: int, W: int) -> torch.Tensor:
+        """Activation workspace of the handle; grown (never inside a graph capture: the wrapper's first call per shape
+        is eager) to svdpp_unet_workspace_bytes of the largest shape seen."""
+        key = (B, F, H, W)
+        if self._ws_shape is None or key not in self._ws_shape:
+            need = self._handle.workspace_bytes(B, F, H, W)
+            if self._ws is None or self._ws.numel() < need:
+                if torch.cuda.is_current_stream_capturing():
+                    raise NativeError("the UNet workspace must be sized by an eager call before CUDA-graph capture")
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device_)
+            self._ws_shape = (self._ws_shape or set()) | {key}
+        return self._ws
+
+    def step_native(self, out, latent, image_latents, uncond_image_latents, enc, ids, gs, *, timestep, in_div, c_v, c_x,
+                    sigma, dt) -> torch.Tensor:
+        """One whole denoising step in one C call (``svdpp_unet_step``; reference svd_unet.py:351-439)."""
+        B, _, F, H, W = latent.shape
+        ws = self._workspace(B, F, H, W)
+        self._handle.step(out, latent, image_latents, uncond_image_latents, enc.contiguous(), ids.contiguous(), gs, ws,
+                          timestep=timestep, in_div=in_div, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt)
+        return out
 
     # ------------------------------------------------------------------ weight packing
     def _g(self, key: str) -> torch.Tensor:
@@ -320,6 +366,8 @@ class NativeUNet(nn.Module):
         del self._ca_wv, self._ca_groups
 
     def weight_bytes(self) -> int:
+        if self._handle is not None:
+            return self._handle.weight_bytes()
         return sum(t.numel() * t.element_size() for t in self._tensors)
 
     # ------------------------------------------------------------------ op helpers
@@ -437,7 +485,7 @@ class NativeUNet(nn.Module):
         qkv = self._linear(n1, P["qkv1"])
         att = native.attn_spatial(self._new(M, C), qkv, n_img=n_img, S=HW, heads=heads, q_off=0, k_off=C,
                                   v_off=2 * C, scale=scale,
-                                  impl=(2 if HW >= 1024 else 0) if self.attn_impl is None else self.attn_impl)
+                                  impl=(self.attn_impl_long if HW >= 1024 else 0) if self.attn_impl is None else self.attn_impl)
         o_, c_ = P["ca"]
         cv = cvs[:, o_:o_ + c_]
         h2 = self._linear(att, P["out1"], r1=h0, rowvec=cv, rv_hw=HW, rv_div=F)
@@ -467,6 +515,12 @@ class NativeUNet(nn.Module):
                      B: int, F: int, H: int, W: int) -> torch.Tensor:
         """x_in: channels-last [B*F*H*W, 8]; t_dev: fp32 [B] on device; enc: [B,1,1024] or [B,1024];
         ids: [B,3].  Returns the channels-last prediction [B*F*H*W, 4]."""
+        if self._handle is not None:
+            out = self._new(x_in.shape[0], self.cfg["out_channels"])
+            self._handle.forward(out, x_in, float(t_dev[0]) if not isinstance(t_dev, float) else t_dev,
+                                 enc.reshape(B, -1).contiguous(), ids.contiguous(), self._workspace(B, F, H, W),
+                                 B=B, F=F, H=H, W=W, nhwc=True)
+            return out
         cfg = self.cfg
         boc = tuple(cfg["block_out_channels"])
         enc2d = enc.reshape(B, -1).contiguous()
@@ -545,6 +599,12 @@ class NativeUNet(nn.Module):
             raise NativeError("NativeUNet.forward needs CUDA tensors (there is no CPU path)")
         B, F, C, H, W = sample.shape
         sample = sample.to(torch.float16).contiguous()
+        if self._handle is not None:
+            out = self._new(B, F, self.cfg["out_channels"], H, W)
+            self._handle.forward(out, sample, float(timestep), encoder_hidden_states.to(torch.float16).reshape(B, -1).contiguous(),
+                                 added_time_ids.to(torch.float16).contiguous(), self._workspace(B, F, H, W),
+                                 B=B, F=F, H=H, W=W)
+            return (out,)
         t_dev = torch.full((B,), float(timestep), dtype=torch.float32, device=sample.device)
         x_in = self._new(B * F * H * W, C)
         native.pack_unet_input(x_in, sample, (F * C * H * W, C * H * W, H * W), C, 1.0, None, None, 0,

@@ -89,6 +89,7 @@ class StableVideoUNet(nn.Module):
 
         device = kwargs.pop("device", "cuda")
         config = kwargs.pop("config", None)
+        orchestrator = kwargs.pop("orchestrator", None)   # "c" (default: csrc/unet.cu) or "python" (per-kernel ctypes launches)
         if model_id.startswith("random-init"):
             seed = int(model_id.split(":", 1)[1]) if ":" in model_id else 0
             sd = random_state_dict(config, seed=seed, device=device)
@@ -104,7 +105,7 @@ class StableVideoUNet(nn.Module):
             raise FileNotFoundError(
                 f"'{model_id}' is not a local checkpoint directory and there is no network access; "
                 "use a local path or 'random-init[:seed]'")
-        unet = NativeUNet(sd, config=config, device=device)
+        unet = NativeUNet(sd, config=config, device=device, orchestrator=orchestrator)
         del sd
         if timesteps is None:
             timesteps = cls._default_timestep_schedule(num_steps=25)
@@ -203,16 +204,23 @@ class StableVideoUNet(nn.Module):
         strides = (C * F * H * W, H * W, F * H * W)  # (b, f, c) element strides of [B,C,F,H,W]
         cfg = self._cfg_on
         nb = 2 * B if cfg else B
+        if cfg and self._cfg_cache is None:
+            self._cfg_cache = (torch.cat([self._uncond_embeddings, self._image_embeddings]).contiguous(),
+                               torch.cat([self._added_time_ids, self._added_time_ids]).contiguous(),
+                               self._guidance_scale_tensor.reshape(-1).contiguous())
+        if hasattr(self.unet, "step_native") and getattr(self.unet, "orchestrator", "") == "c":
+            # the whole step behind the C ABI: one svdpp_unet_step call (pack, UNet, guidance + Euler)
+            enc, ids, gs = self._cfg_cache if cfg else (self._image_embeddings, self._added_time_ids, None)
+            return self.unet.step_native(torch.empty_like(latent), latent, self._image_latents,
+                                         self._uncond_image_latents if cfg else None, enc, ids, gs,
+                                         timestep=float(self.scheduler_timesteps[step]), in_div=in_div, c_v=c_v, c_x=c_x,
+                                         sigma=sigma, dt=dt)
         x_in = torch.empty((nb * F * H * W, 2 * C), dtype=torch.float16, device=dev)
         if cfg:
             native.pack_unet_input(x_in[:M], latent, strides, C, in_div, self._uncond_image_latents, strides, C,
                                    B=B, F=F, H=H, W=W)
             native.pack_unet_input(x_in[M:], latent, strides, C, in_div, self._image_latents, strides, C,
                                    B=B, F=F, H=H, W=W)
-            if self._cfg_cache is None:
-                self._cfg_cache = (torch.cat([self._uncond_embeddings, self._image_embeddings]).contiguous(),
-                                   torch.cat([self._added_time_ids, self._added_time_ids]).contiguous(),
-                                   self._guidance_scale_tensor.reshape(-1).contiguous())
             enc, ids, gs = self._cfg_cache
         else:
             native.pack_unet_input(x_in, latent, strides, C, in_div, self._image_latents, strides, C,

@@ -20,11 +20,13 @@ GEMM_BN = 160  # N tile of the tcgen05 GEMM; weights are padded / GEGLU-interlea
 EXPORTED_SYMBOLS = (
     "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_set_tuning", "svdpp_get_tuning",
     "svdpp_gemm_f16",
-    "svdpp_attn_spatial_f16", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
+    "svdpp_attn_spatial_f16", "svdpp_debug_attn_trace", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
     "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_linear_small_grouped",
     "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
     "svdpp_euler_vpred_step", "svdpp_dummy_unet_step",
+    "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
+    "svdpp_unet_forward", "svdpp_unet_forward_nhwc", "svdpp_unet_step", "svdpp_unet_last_launches", "svdpp_unet_destroy",
 )
 
 
@@ -67,6 +69,29 @@ class AttnDesc(C.Structure):
     ]
 
 
+UNET_MAX_LEVELS = 8
+
+
+class UNetConfig(C.Structure):
+    """``svdpp_unet_config`` (include/svdpp.h)."""
+    _fields_ = [
+        ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("n_levels", C.c_int32),
+        ("block_out_channels", C.c_int32 * UNET_MAX_LEVELS), ("down_attn", C.c_int32 * UNET_MAX_LEVELS),
+        ("num_attention_heads", C.c_int32 * UNET_MAX_LEVELS),
+        ("layers_per_block", C.c_int32), ("cross_attention_dim", C.c_int32), ("addition_time_embed_dim", C.c_int32),
+        ("projection_class_embeddings_input_dim", C.c_int32),
+        ("eps_down_attn", C.c_float), ("eps_down", C.c_float), ("eps_mid", C.c_float), ("eps_up", C.c_float),
+        ("eps_transformer", C.c_float), ("eps_out", C.c_float),
+        ("gemm_impl", C.c_int32), ("attn_impl", C.c_int32), ("attn_impl_long", C.c_int32),
+    ]
+
+
+class TensorDesc(C.Structure):
+    """``svdpp_tensor_desc``."""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 5),
+                ("dtype", C.c_int32)]
+
+
 _lib = None
 
 # Number of libsvdpp kernels launched through this binding (bench.py reports it as gpu_launches).
@@ -94,6 +119,7 @@ def _bind(lib):
     lib.svdpp_groupnorm_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.svdpp_gemm_f16.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_void_p]
     lib.svdpp_attn_spatial_f16.argtypes = [C.POINTER(AttnDesc), C.c_int, C.c_void_p]
+    lib.svdpp_debug_attn_trace.argtypes = [C.c_void_p]
     lib.svdpp_attn_temporal_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             C.c_void_p]
@@ -122,6 +148,22 @@ def _bind(lib):
                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.svdpp_dummy_unet_step.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_int32] * 6 + [C.c_void_p]
+    lib.svdpp_unet_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(UNetConfig)]
+    lib.svdpp_unet_load_weights.argtypes = [C.c_void_p, C.POINTER(TensorDesc), C.c_int]
+    lib.svdpp_unet_weight_bytes.restype = C.c_size_t
+    lib.svdpp_unet_weight_bytes.argtypes = [C.c_void_p]
+    lib.svdpp_unet_workspace_bytes.restype = C.c_size_t
+    lib.svdpp_unet_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    fwd = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.svdpp_unet_forward.argtypes = fwd
+    lib.svdpp_unet_forward_nhwc.argtypes = fwd
+    lib.svdpp_unet_step.argtypes = [C.c_void_p] * 7 + [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_size_t,
+                                                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.svdpp_unet_last_launches.restype = C.c_longlong
+    lib.svdpp_unet_last_launches.argtypes = [C.c_void_p]
+    lib.svdpp_unet_destroy.restype = None
+    lib.svdpp_unet_destroy.argtypes = [C.c_void_p]
     return lib
 
 
@@ -460,3 +502,94 @@ def dummy_unet_step(out, x, w1, b1, w2, b2, ln_g, ln_b, ln_eps, tanh_scale, hidd
                                         out.data_ptr(), B, Cc, Ch, F, H, W, _stream()), "svdpp_dummy_unet_step")
     _count(3)
     return out
+
+
+# ------------------------------------------------------------------------------------------ whole-UNet handle
+class UNetHandle:
+    """Owner of one ``svdpp_unet`` (include/svdpp.h): create + load_weights here, forward / step below; destroyed with
+    the object.  The activation workspace is a torch tensor the caller keeps (one per handle is enough)."""
+
+    def __init__(self, cfg: dict, state_dict, *, gemm_impl: int = 3, attn_impl: Optional[int] = None,
+                 attn_impl_long: int = 0):
+        lib = load()
+        c = UNetConfig()
+        boc = tuple(cfg["block_out_channels"])
+        if len(boc) > UNET_MAX_LEVELS:
+            raise NativeError(f"at most {UNET_MAX_LEVELS} resolution levels")
+        c.in_channels, c.out_channels, c.n_levels = cfg["in_channels"], cfg["out_channels"], len(boc)
+        for i, v in enumerate(boc):
+            c.block_out_channels[i] = v
+            c.down_attn[i] = 1 if tuple(cfg["down_attn"])[i] else 0
+            c.num_attention_heads[i] = tuple(cfg["num_attention_heads"])[i]
+        c.layers_per_block = cfg["layers_per_block"]
+        c.cross_attention_dim = cfg["cross_attention_dim"]
+        c.addition_time_embed_dim = cfg["addition_time_embed_dim"]
+        c.projection_class_embeddings_input_dim = cfg["projection_class_embeddings_input_dim"]
+        eps = cfg["norm_eps"]
+        c.eps_down_attn, c.eps_down, c.eps_mid, c.eps_up = eps["down_attn"], eps["down"], eps["mid"], eps["up"]
+        c.eps_transformer, c.eps_out = eps["transformer"], eps["out"]
+        c.gemm_impl = gemm_impl
+        c.attn_impl = -1 if attn_impl is None else attn_impl
+        c.attn_impl_long = attn_impl_long
+        h = C.c_void_p()
+        _check(lib.svdpp_unet_create(C.byref(h), C.byref(c)), "svdpp_unet_create")
+        self._h = h
+        self._lib = lib
+        keep = []                      # fp16 / contiguous copies must outlive the call
+        descs = (TensorDesc * len(state_dict))()
+        for i, (name, t) in enumerate(state_dict.items()):
+            if not t.is_cuda:
+                raise NativeError("svdpp_unet_load_weights needs CUDA tensors")
+            if name.endswith("mix_factor") and t.dtype == torch.float32:
+                t, dt = t.detach().contiguous(), 1
+            else:
+                t, dt = t.detach().to(torch.float16).contiguous(), 0
+            keep.append(t)
+            descs[i].name = name.encode()
+            descs[i].data = t.data_ptr()
+            descs[i].ndim = t.dim()
+            for j, d in enumerate(t.shape):
+                descs[i].shape[j] = d
+            descs[i].dtype = dt
+        try:
+            _check(lib.svdpp_unet_load_weights(h, descs, len(state_dict)), "svdpp_unet_load_weights")
+        except NativeError:
+            lib.svdpp_unet_destroy(h)
+            self._h = None
+            raise
+        del keep
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and self._lib is not None:
+            self._lib.svdpp_unet_destroy(h)
+
+    def weight_bytes(self) -> int:
+        return int(self._lib.svdpp_unet_weight_bytes(self._h))
+
+    def workspace_bytes(self, B: int, F: int, H: int, W: int) -> int:
+        n = int(self._lib.svdpp_unet_workspace_bytes(self._h, B, F, H, W))
+        if n == 0:
+            raise NativeError(f"svdpp_unet_workspace_bytes failed: {self._lib.svdpp_last_error().decode()}")
+        return n
+
+    def _done(self, rc: int, what: str) -> None:
+        _check(rc, what)
+        _count(int(self._lib.svdpp_unet_last_launches(self._h)))
+
+    def forward(self, out, sample, timestep: float, enc, ids, ws, *, B, F, H, W, nhwc: bool = False) -> None:
+        for t in (out, sample, enc, ids):
+            _req(t)
+        fn = self._lib.svdpp_unet_forward_nhwc if nhwc else self._lib.svdpp_unet_forward
+        self._done(fn(self._h, sample.data_ptr(), float(timestep), enc.data_ptr(), ids.data_ptr(), out.data_ptr(),
+                      ws.data_ptr(), ws.numel() * ws.element_size(), B, F, H, W, _stream()), "svdpp_unet_forward")
+
+    def step(self, out, latent, image_latents, uncond_image_latents, enc, ids, gs, ws, *, timestep, in_div, c_v, c_x,
+             sigma, dt) -> None:
+        for t in (out, latent, image_latents, enc, ids):
+            _req(t)
+        B, _, F, H, W = latent.shape
+        self._done(self._lib.svdpp_unet_step(self._h, latent.data_ptr(), image_latents.data_ptr(),
+                                             _ptr(uncond_image_latents), enc.data_ptr(), ids.data_ptr(), _ptr(gs),
+                                             float(timestep), in_div, c_v, c_x, sigma, dt, out.data_ptr(), ws.data_ptr(),
+                                             ws.numel() * ws.element_size(), B, F, H, W, _stream()), "svdpp_unet_step")
