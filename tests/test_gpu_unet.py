@@ -244,6 +244,34 @@ def test_norm_eps_table_reaches_the_kernels():
     assert all(r["eps"] == 1e-5 for blk in nat5.up for r in blk["res"])
 
 
+def test_whole_stage_graph_matches_per_step_execution():
+    """a stage's slice of the schedule as ONE CUDA graph (``forward_steps`` / ``use_stage_graph``)
+    gives the same bits as step-by-step execution, with and without guidance, and through PipelineStage."""
+    from vdpp_b200.models import StableVideoUNet
+    from vdpp_b200.pipeline import LatentSpec, PipelineConfig, PipelineStage
+    _, nat = kc._tiny_pair()
+    dev = torch.device("cuda")
+    model = StableVideoUNet(unet=nat, timesteps=StableVideoUNet._default_timestep_schedule(25)).to(dev)
+    for gs in (None, 2.5):
+        torch.manual_seed(5)
+        model.set_dummy_conditioning(1, 3, 16, 16, dev, guidance_scale=gs)
+        xs = [torch.randn(1, 4, 3, 16, 16, device=dev).half() * model.init_noise_sigma for _ in range(3)]
+        steps = [3, 4, 5, 6]
+        model.use_stage_graph = False
+        want = []
+        for x in xs:
+            for s in steps:
+                x = model(x, s)
+            want.append(x)
+        model.use_stage_graph = True
+        got = [model.forward_steps(x, steps) for x in xs]          # eager warm-up, capture, replay
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        spec = LatentSpec(shape=xs[0].shape, dtype=torch.float16, device=dev)
+        stage = PipelineStage(model, PipelineConfig(total_steps=4, world_size=1, rank=0, timesteps=steps, latent_spec=spec))
+        assert torch.equal(stage.run(xs[1]), want[1])
+    assert any(k[0] == "stage" for k in model._graphs)
+
+
 def test_conditioning_shape_mismatch_raises():
     """A guidance ramp / image latents / embeddings whose shape does not match the latent must raise instead of letting
     the kernels index past the end (the reference fails with a broadcast error there)."""

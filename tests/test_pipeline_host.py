@@ -201,3 +201,38 @@ def test_ring_placement_matches_single_process():
     5 videos (a partial last round), bit-identical to running each video alone."""
     assert _run_ring(4, 25, 5) == _single_process(25, 5)
     assert _run_ring(2, 28, 4) == _single_process(28, 4)
+
+
+def test_stage_runner_hands_whole_slice_to_forward_steps():
+    """A model that offers ``forward_steps`` and sets ``use_stage_graph`` gets its stage's slice of the schedule in ONE
+    call (the whole-stage CUDA graph of StableVideoUNet); without the flag the reference's per-step loop runs."""
+    import torch
+    from vdpp_b200.pipeline import LatentSpec, PipelineConfig, PipelineStage
+
+    class M(torch.nn.Module):
+        use_stage_graph = False
+
+        def __init__(self):
+            super().__init__()
+            self.calls = []
+
+        def forward(self, x, step):
+            self.calls.append(("step", step))
+            return x + step
+
+        def forward_steps(self, x, steps):
+            self.calls.append(("slice", tuple(steps)))
+            for s in steps:
+                x = x + s
+            return x
+
+    spec = LatentSpec(shape=torch.Size((1, 2)), dtype=torch.float32, device=torch.device("cpu"))
+    ts = [9, 7, 5, 3]
+    outs = []
+    for flag in (False, True):
+        m = M()
+        m.use_stage_graph = flag
+        st = PipelineStage(m, PipelineConfig(total_steps=4, world_size=1, rank=0, timesteps=ts, latent_spec=spec))
+        outs.append(st.run(torch.zeros(1, 2)))
+        assert m.calls == ([("slice", (9, 7, 5, 3))] if flag else [("step", t) for t in ts])
+    assert torch.equal(outs[0], outs[1])

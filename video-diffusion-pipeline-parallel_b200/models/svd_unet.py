@@ -47,6 +47,7 @@ class StableVideoUNet(nn.Module):
         self._guidance_scale_tensor = None
         # execution options (extensions)
         self.use_cuda_graph = False
+        self.use_stage_graph = False          # forward_steps(): one CUDA graph for a whole stage's step slice
         self._graphs: Dict[tuple, tuple] = {}
         self._graph_pool = None
         self._warm: set = set()
@@ -266,6 +267,59 @@ class StableVideoUNet(nn.Module):
         if hasattr(self.unet, "forward_nhwc"):
             return self._step_native(latent, step)
         return self._step_foreign(latent, step)
+
+    @torch.inference_mode()
+    def forward_steps(self, latent: torch.Tensor, steps: Sequence[int]) -> torch.Tensor:
+        """All of ``steps`` on one latent: ``for s in steps: latent = self(latent, s)`` - what
+        ``PipelineStage._run_local_steps`` does with a stage's slice of the schedule (reference pipeline.py:86-98).
+        With ``use_stage_graph`` the whole slice (every launch of every step, ~740 per step) is ONE CUDA graph per
+        (slice, shape), replayed with a single launch call per video and stage."""
+        steps = tuple(int(s) for s in steps)
+        if not steps:
+            return latent
+        if not self.use_stage_graph:
+            for s in steps:
+                latent = self.forward(latent, s)
+            return latent
+        if not self._conditioning_set:
+            raise RuntimeError("Conditioning not set. Call set_conditioning() or "
+                               "set_dummy_conditioning() before forward().")
+        for s in steps:
+            if not (0 <= s < len(self.timesteps)):
+                raise ValueError(f"Step {s} out of range [0, {len(self.timesteps)})")
+        from ..native import NativeError
+        if not latent.is_cuda:
+            raise NativeError("StableVideoUNet.forward needs a CUDA latent: this build has no CPU path")
+        latent = latent.to(torch.float16).contiguous()
+        self._check_conditioning_shapes(latent)
+        shape_key = tuple(latent.shape)
+        if shape_key not in self._warm:           # first call per shape runs eagerly (fills caches, sizes workspaces)
+            self._warm.add(shape_key)
+            for s in steps:
+                latent = self._step(latent, s)
+            return latent
+        key = ("stage", steps, shape_key)
+        if key not in self._graphs:
+            from .. import native
+            g_in = latent.clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            before = native.LAUNCHES
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                x = g_in
+                for s in steps:
+                    x = self._step(x, s)
+            n_kernels = native.LAUNCHES - before
+            native.LAUNCHES = before
+            self._graphs[key] = (graph, g_in, x, n_kernels)
+        graph, g_in, g_out, n_kernels = self._graphs[key]
+        g_in.copy_(latent)
+        graph.replay()
+        from .. import native
+        native.LAUNCHES += n_kernels
+        return g_out.clone()
 
     @torch.inference_mode()
     def forward(self, latent: torch.Tensor, step: int) -> torch.Tensor:

@@ -131,8 +131,15 @@ class PipelineStage:
         """The inner hot loop (reference ``pipeline.py:86-98``): ``model(latent, timesteps[i])``."""
         if len(self._local_timesteps) != self.step_range.count:
             raise RuntimeError("Local timestep slice length mismatch with step range.")
+        return self._run_steps(latent, self._local_timesteps)
+
+    def _run_steps(self, latent: torch.Tensor, steps: Sequence[int]) -> torch.Tensor:
+        """``model(latent, step)`` for every step of a slice; a model that offers ``forward_steps`` and asks for it
+        (``use_stage_graph``) gets the whole slice in one call (one CUDA graph per stage: SURVEY 8(f) rank 2)."""
+        if getattr(self.model, "use_stage_graph", False) and hasattr(self.model, "forward_steps"):
+            return self.model.forward_steps(latent, steps)
         verbose = self.logger.isEnabledFor(logging.INFO)
-        for step in self._local_timesteps:
+        for step in steps:
             t0 = time.time() if verbose else 0.0
             latent = self.model(latent, step)
             if verbose:
@@ -209,8 +216,7 @@ class PipelineStage:
                         raise ValueError("input_supplier returned None")
                     cur = cur.to(cfg.latent_spec.device)
                 if exists:
-                    for step in cfg.timesteps[stages[t].start: stages[t].end]:
-                        cur = self.model(cur, step)
+                    cur = self._run_steps(cur, cfg.timesteps[stages[t].start: stages[t].end])
                 if t == W - 1:
                     if exists:
                         # an empty last stage would append the receive slot itself (rewritten two hops later)
