@@ -58,6 +58,9 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true",
                    help="enqueue every launch eagerly instead of replaying one CUDA graph per denoising step (within "
                         "+-1 %%: the host runs ~740 launches per step ahead of the GPU either way)")
+    p.add_argument("--transport", default="nccl", choices=["nccl", "peer"],
+                   help="N>1 latent handoff: 'nccl' = dist.send/recv (isend/irecv waited on the stream), 'peer' = the next "
+                        "stage's peer-mapped receive slot written by the producer's Euler kernel + flag (distributed/handoff.py)")
     p.add_argument("--force-graph", action="store_true", help="N=1: skip the eager-vs-graph measurement, use graphs")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-library-baseline", action="store_true")
@@ -333,7 +336,7 @@ def main() -> None:
     spec = LatentSpec(shape=shape, dtype=torch.float16, device=dev)
     cfg = PipelineConfig(total_steps=T, world_size=world, rank=rank, timesteps=list(range(T)), latent_spec=spec,
                          allow_uneven=True)
-    stage = PipelineStage(model=model, config=cfg)
+    stage = PipelineStage(model=model, config=cfg, transport=args.transport if world > 1 else "nccl")
     n_videos = K * world
     last = rank == world - 1
 
@@ -452,19 +455,10 @@ def main() -> None:
         torch.cuda.synchronize()
     else:
         for i in range(n_videos):
-            if rank == 0:
-                lat = supply_from_host(i)
-            else:
-                work, buf = stage._post_recv()
-                work.wait()
-                lat = buf if stage.step_range.count else buf.clone()
-            lat = stage._run_local_steps(lat)
+            lat = stage._process_single_latent(supply_from_host(i) if rank == 0 else None, sample_idx=i)
             if last:
                 host_out.copy_(lat, non_blocking=True)
                 torch.cuda.synchronize()
-            else:
-                stage._send_latent(lat, blocking=False)
-                stage._drain_send()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -549,7 +543,7 @@ def main() -> None:
                             f"{'CFG %.1f batch 2' % args.guidance_scale if args.guidance_scale else 'no CFG'}",
                 "videos_timed": n_videos, "stage_sizes": stage_sizes(T, world),
                 "parallelism": (f"step-pipeline x{world}, {'rotating (ring)' if ring else 'fixed (reference)'} stage "
-                                f"placement") if world > 1 else "single GPU",
+                                f"placement, handoff via {stage.transport}") if world > 1 else "single GPU",
                 "cuda_graph": model.use_cuda_graph,
                 "l2": "per-step working set (3 GB weights + >10 GB activations) exceeds the 126 MB L2; no flush needed",
             },

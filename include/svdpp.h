@@ -212,6 +212,28 @@ int svdpp_euler_vpred_step(const void* latent, const void* v_a, const void* v_co
                            int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
                            int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, svdpp_stream stream);
 
+/* Stage-to-stage latent handoff over peer-mapped memory (NVLink), replacing the dist.send / dist.recv pair of reference
+ * src/pipeline/pipeline.py:75-84.  The producer's LAST local step writes its result straight into a buffer that lives on
+ * the next stage's GPU (`out` of svdpp_euler_vpred_step_signal / svdpp_unet_step_handoff is that peer-mapped pointer) and
+ * the same kernel raises the consumer's flag when all of its stores are visible; the consumer's stream waits for the flag
+ * with svdpp_flag_wait before its first kernel touches the buffer, and hands the slot back with svdpp_flag_set on the
+ * producer's acknowledge flag.  No NCCL kernel, no lock-step between ranks, no extra copy.
+ *   done_counter  LOCAL device uint32, zero before the first use (the kernel re-arms it)
+ *   ready_flag    uint32 in the CONSUMER's memory (peer-mapped); set to flag_value by a release store at system scope
+ * svdpp_flag_wait: one thread spins (acquire, system scope) until *flag == value, then stores reset_to if reset != 0; after
+ * timeout_s seconds (<= 0: 600) it prints a message and traps, so a protocol bug becomes a CUDA error, not a hung GPU. */
+typedef struct svdpp_handoff {
+  void* done_counter;
+  void* ready_flag;
+  uint32_t flag_value;
+} svdpp_handoff;
+int svdpp_euler_vpred_step_signal(const void* latent, const void* v_a, const void* v_cond, const void* gs,
+                                  int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
+                                  int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, const svdpp_handoff* ho /* or NULL */,
+                                  svdpp_stream stream);
+int svdpp_flag_wait(void* flag, uint32_t value, int32_t reset, uint32_t reset_to, int32_t timeout_s, svdpp_stream stream);
+int svdpp_flag_set(void* flag, uint32_t value, svdpp_stream stream);
+
 /* DummyUNet step (reference src/models/dummy_unet.py:37-59), fp32, [B, C, F, H, W]:
  *   out = x + tanh_scale * conv3d(silu(conv3d(x, w1, b1)), w2, b2) + layernorm_C(x) */
 int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -291,6 +313,12 @@ int svdpp_unet_step(svdpp_unet* u, const void* latent, const void* image_latents
                     const void* enc, const void* added_time_ids, const void* gs, float timestep, float in_div, float c_v,
                     float c_x, float sigma, float dt, void* out, void* workspace, size_t workspace_bytes, int B, int F, int H,
                     int W, svdpp_stream stream);
+/* svdpp_unet_step whose result goes to `out` AND raises a flag when it is complete (see svdpp_handoff): `out` is then the
+ * next stage's peer-mapped receive slot.  ho == NULL: identical to svdpp_unet_step. */
+int svdpp_unet_step_handoff(svdpp_unet* u, const void* latent, const void* image_latents, const void* uncond_image_latents,
+                            const void* enc, const void* added_time_ids, const void* gs, float timestep, float in_div,
+                            float c_v, float c_x, float sigma, float dt, void* out, void* workspace, size_t workspace_bytes,
+                            int B, int F, int H, int W, const svdpp_handoff* ho, svdpp_stream stream);
 /* kernels launched by the last forward / step on this handle (bench.py's gpu_launches) */
 long long svdpp_unet_last_launches(const svdpp_unet* u);
 void svdpp_unet_destroy(svdpp_unet* u);

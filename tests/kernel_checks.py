@@ -357,6 +357,30 @@ def euler(cfg=True, step=3, n=25):
     return dict(max_err=err, tol=0.0, ok=bool(ok))
 
 
+def handoff_flags(cfg=True):
+    """The flag-signalled handoff on ONE device (set, then wait: a wait that had to block on another launch of the same
+    GPU is exactly what must not be built): the Euler kernel with a handoff writes `out` and raises the flag from its
+    last block; svdpp_flag_wait then returns at once, re-arms the flag, and the completion counter is back at zero."""
+    B, C, Fr, H, W = 1, 4, 5, 24, 40
+    lat = (_rand(B, C, Fr, H, W, seed=1).float() * 50).half()
+    v = _rand(B, Fr, H, W, C, seed=2)
+    vc = _rand(B, Fr, H, W, C, seed=3) if cfg else None
+    gs = torch.linspace(1.0, 3.0, Fr, device=DEV).half() if cfg else None
+    kw = dict(v_cond=vc, gs=gs, v_nhwc=True, c_v=-0.99, c_x=1.5, sigma=0.7, dt=-0.2)
+    want = native.euler_vpred_step(torch.empty_like(lat), lat, v, **kw)
+    flags = torch.zeros(4, dtype=torch.int32, device=DEV)
+    done = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ok = True
+    for rep in range(3):      # the counter re-arms itself: three hand-overs through the same flag
+        out = torch.full_like(lat, float("nan"))
+        native.euler_vpred_step(out, lat, v, handoff=(done.data_ptr(), flags[1:].data_ptr(), 1), **kw)
+        native.flag_wait(flags[1:].data_ptr(), 1, reset_to=0, timeout_s=5)
+        native.flag_set(flags[2:].data_ptr(), 7 + rep)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(out, want) and flags.tolist() == [0, 0, 7 + rep, 0] and int(done.item()) == 0
+    return dict(max_err=0.0 if ok else 1.0, tol=0.0, ok=bool(ok))
+
+
 def dummy_unet(C=4, Ch=16, step=7):
     from vdpp_b200.models import DummyUNet
     torch.manual_seed(0)
@@ -386,6 +410,8 @@ ALL_CHECKS = {
     "layernorm_1280": lambda: layernorm(M=33, C=1280, add=False),
     "layernorm_640": lambda: layernorm(M=37, C=640, add=True),
     "layernorm_generic": lambda: layernorm(M=19, C=128, add=True),
+    "handoff_flags_cfg": lambda: handoff_flags(True),
+    "handoff_flags_nocfg": lambda: handoff_flags(False),
     "groupnorm": lambda: groupnorm(),
     # variance ~ 4e-6: eps = 1e-6 and 1e-5 give outputs 1.7x apart, so the scalar must reach the kernel unchanged
     "groupnorm_small_var_eps_1e6": lambda: groupnorm(eps=1e-6, in_scale=1e-3),
@@ -580,6 +606,18 @@ for _n in ("pair320_splitk_12way", "pair320_splitk_5way", "pair320_splitk_6way_b
 for _n in ("pair320_splitk_12way", "pair320_splitk_conv"):
     ALL_CHECKS["nosplit_" + _n] = _tuned(ALL_CHECKS[_n], splitk=0)
 ALL_CHECKS["tc_gemm_geglu_tail"] = lambda: gemm_geglu(M=1000, C=320, impl=3)
+# traversal direction ("reverse": rows walked from the end - the L2-friendly order after a forward producer); results must not
+# depend on it.  GroupNorm: 1 = statistics from the end / apply forward, 2 = the other way round
+for _n in ("tc_gemm_linear", "tc_gemm_many_tiles", "pair256_gemm_many_tiles", "pair320_gemm_many_tiles", "pair256_gemm_mtail_odd",
+           "pair320_gemm_mtail_odd", "pair256_gemm_geglu_320", "tc_conv3x3_w32", "pair320_conv3x3_w32", "tc_conv_temporal",
+           "tc_conv3x3_stride2_w32", "tc_conv_up2x_w32", "pair320_splitk_12way", "pair320_splitk_conv", "bn128_gemm_linear",
+           "layernorm", "layernorm_640", "layernorm_1280", "layernorm_generic", "groupnorm", "groupnorm_cat",
+           "groupnorm_cat_1920"):
+    if _n in ALL_CHECKS:
+        ALL_CHECKS["rev_" + _n] = _tuned(ALL_CHECKS[_n], reverse=1)
+for _n in ("groupnorm", "groupnorm_cat", "groupnorm_cat_1920"):
+    if _n in ALL_CHECKS:
+        ALL_CHECKS["rev2_" + _n] = _tuned(ALL_CHECKS[_n], reverse=2)
 
 
 # ------------------------------------------------------------------------------------------ whole UNet
@@ -673,6 +711,9 @@ UNET_CHECKS = {
     "svd_steps_tc_graph_pyorch": lambda: svd_steps(graph=True, orchestrator="python"),
 }
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
+UNET_CHECKS["unet_tiny_tc_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_tc"], zigzag=1)      # producer -> consumer direction flips
+UNET_CHECKS["unet_tiny_pair256_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], zigzag=1)
+UNET_CHECKS["svd_steps_tc_cfg_zigzag"] = _tuned(UNET_CHECKS["svd_steps_tc_cfg"], zigzag=1)
 UNET_CHECKS["unet_tiny_pair256_pdl"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], pdl=1)
 UNET_CHECKS["unet_tiny_pair256_r1ldg"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], tma_r1=0)
 UNET_CHECKS["unet_tiny_tc_dma"] = _tuned(UNET_CHECKS["unet_tiny_tc"], epi_dma=2)

@@ -89,6 +89,24 @@ def test_c_orchestration_matches_python_orchestration_bit_for_bit(cfg_over, gemm
         assert torch.equal(outs[0], outs[1])
 
 
+def test_zigzag_traversal_changes_no_bit():
+    """svdpp_set_tuning("zigzag", 1): every row-streaming kernel starts at the end its producer wrote last.  An execution
+    order, not an arithmetic change: the operator's output is bit-identical."""
+    from vdpp_b200 import native
+    _, nat = kc._tiny_pair(PAIR256, 3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    sample = torch.randn(2, 3, 8, 16, 32, device="cuda", generator=g).half()
+    enc = torch.randn(2, 1, 1024, device="cuda", generator=g).half()
+    ids = torch.tensor([[5.0, 127.0, 0.02]], device="cuda").half().repeat(2, 1)
+    base = nat(sample, torch.tensor(0.3), enc, ids)[0]
+    old = native.set_tuning("zigzag", 1)
+    try:
+        zz = nat(sample, torch.tensor(0.3), enc, ids)[0]
+    finally:
+        native.set_tuning("zigzag", old)
+    assert torch.equal(base, zz)
+
+
 def test_unet_c_abi_five_calls():
     """one forward of the UNet operator with nothing but svdpp_unet_create / _load_weights /
     _workspace_bytes / _forward / _destroy (torch only provides device memory), against the Python orchestration."""

@@ -81,13 +81,16 @@ __device__ __forceinline__ void gn_bulk_load(uint32_t dst, const void* src, uint
 __global__ void __launch_bounds__(512)
 gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int pix,
                   int n_chunks, int n_items, int ipc, int n_slots, float2* partial, double2* imgsum, unsigned* counters,
-                  int frames_per_stat, float count, float eps, float2* __restrict__ stats) {
+                  int frames_per_stat, float count, float eps, float2* __restrict__ stats, int rev) {
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
   extern __shared__ __align__(128) uint8_t gn_smem[];
   __shared__ int s_last;
   __shared__ __align__(8) uint64_t s_bar[8];
-  const int begin = blockIdx.x * ipc;
+  // rev: the blocks that are scheduled first take the LAST items (the end of the tensor, which the producing kernel
+  // wrote last and which is therefore still in L2); the item -> partial-slot mapping is unchanged
+  const int vblk = rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int begin = vblk * ipc;
   const int end = min(begin + ipc, n_items);
   if (begin >= end) return;
   const int C = C1 + C2;
@@ -150,7 +153,7 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
           b += __shfl_xor_sync(0xffffffffu, b, o);
         }
         if (j == 0) {
-          const int slot = static_cast<int>(blockIdx.x) - first_blk;
+          const int slot = vblk - first_blk;
           partial[(static_cast<long long>(n) * max_slots + slot) * GN_GROUPS + g] = make_float2(a, b);
           __threadfence();
         }
@@ -269,14 +272,14 @@ gn_partial_kernel(const __half* __restrict__ x1, int C1, const __half* __restric
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, const float2* __restrict__ stats,
-                __half* __restrict__ out, int HW, int pix, int frames_per_stat, int silu) {
+                __half* __restrict__ out, int HW, int pix, int frames_per_stat, int silu, int rev) {
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
   const int C = C1 + C2;
   const int rows = blockDim.y;
   const int c0 = threadIdx.x * 8;
-  const int n = blockIdx.y;
-  const int p0 = blockIdx.x * pix;
+  const int n = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int p0 = (rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x)) * pix;
   const int p1 = min(p0 + pix, HW);
   const int cpg = C / GN_GROUPS;
   const float2* st = stats + (n / frames_per_stat) * GN_GROUPS;
@@ -322,11 +325,11 @@ constexpr int LN_MAX_VEC = 5;  // per lane: 5 * 8 * 32 = 1280 channels max
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
                  int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                 __half* __restrict__ out, long long ldo, int M, int C, float eps) {
+                 __half* __restrict__ out, long long ldo, int M, int C, float eps, int rev) {
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
+  const long long m = static_cast<long long>(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (m >= M) return;
   const int nvec = C >> 3;
   const __half* xr = x + m * ldx;
@@ -387,14 +390,14 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ addvec, int add_hw,
                       int add_mod, const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                      __half* __restrict__ out, long long ldo, int M, float eps) {
+                      __half* __restrict__ out, long long ldo, int M, float eps, int rev) {
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
   constexpr int RPW = 32 / LPR;
   constexpr int C = 40 * LPR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPR, li = lane % LPR;
-  const long long m = (static_cast<long long>(blockIdx.x) * 8 + warp) * RPW + sub;
+  const long long m = (static_cast<long long>(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp) * RPW + sub;
   const bool active = m < M;
   const __half* xr = x + (active ? m : 0) * ldx;
   const __half* ar = addvec ? addvec + static_cast<long long>(((active ? m : 0) / add_hw) % add_mod) * C : nullptr;
@@ -662,7 +665,8 @@ __global__ void nhwc_to_bfchw_kernel(const __half* __restrict__ x, __half* __res
 __global__ void euler_vpred_kernel(const __half* __restrict__ latent, const __half* __restrict__ va,
                                    const __half* __restrict__ vc, const __half* __restrict__ gs, int v_nhwc,
                                    float c_v, float c_x, float sigma, float dt, __half* __restrict__ out, int B,
-                                   int C, int F, int HW) {
+                                   int C, int F, int HW, unsigned* done_counter, unsigned* ready_flag,
+                                   unsigned flag_value) {
   pdl_launch_dependents();  // programmatic dependent launch: see ptx.cuh
   pdl_wait();
   const long long total = static_cast<long long>(B) * F * HW;
@@ -689,6 +693,49 @@ __global__ void euler_vpred_kernel(const __half* __restrict__ latent, const __ha
       out[li] = __float2half_rn(__fadd_rn(x, __fmul_rn(d, dt)));
     }
   }
+  // Stage-to-stage handoff fused into the producer: `out` may be a peer-mapped buffer on the next stage's GPU (the
+  // stores above then travel over NVLink).  Once every block's stores are visible system-wide, the last block to finish
+  // raises the consumer's flag with a release store; the consumer's svdpp_flag_wait kernel acquires it.
+  if (ready_flag != nullptr) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned old = atomicAdd(done_counter, 1u);
+      if (old == gridDim.x - 1) {
+        *done_counter = 0u;   // re-armed for the next launch on this stream
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_flag), "r"(flag_value) : "memory");
+      }
+    }
+  }
+}
+
+// one thread: spin until *flag == value (acquire, system scope: the flag is written by another GPU), then optionally
+// re-arm it.  Bounded: after `timeout_ns` it reports and traps instead of hanging the stream for ever.
+__global__ void flag_wait_kernel(unsigned* flag, unsigned value, int reset, unsigned reset_to, unsigned long long timeout_ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned v;
+  unsigned spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == value) break;
+    if ((++spins & 1023u) == 0u) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        printf("svdpp: flag_wait timeout: flag=%p value=%u wanted=%u\n", static_cast<void*>(flag), v, value);
+        __trap();
+      }
+    }
+    __nanosleep(200);
+  }
+  if (reset) *flag = reset_to;
+}
+
+__global__ void flag_set_kernel(unsigned* flag, unsigned value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
 // ------------------------------------------------------------------------------------ DummyUNet
@@ -797,6 +844,14 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   SVDPP_CHECK_ARG(n_img <= GN_MAX_STATS, "groupnorm: more than %d images", GN_MAX_STATS);
   const int pix = gn_pixels_per_block(n_img, HW, C);
   const int n_chunks = (HW + pix - 1) / pix;
+  // traversal direction (svdpp_set_tuning("reverse")): the statistics pass starts at the end of the tensor the
+  // producer has just written when rev = 1, and the apply pass then runs the other way - it starts where the
+  // statistics pass stopped, i.e. on the part of the input that is hot in L2 now
+  // "reverse": 0 = both passes forward; 1 = statistics from the end, apply forward; 2 = statistics forward, apply from the end
+  const int rev_mode = tuning().reverse;
+  const int rev = rev_mode == 1 ? 1 : 0;
+  int rev_apply = rev_mode == 2 ? 1 : 0;
+  if (rev_mode != 0 && tuning().reverse_gn_apply_same) rev_apply ^= 1;
   unsigned* counters = static_cast<unsigned*>(workspace);
   double2* imgsum = reinterpret_cast<double2*>(static_cast<uint8_t*>(workspace) + GN_COUNTER_BYTES);
   float2* partial = reinterpret_cast<float2*>(imgsum + static_cast<size_t>(n_img) * GN_GROUPS);
@@ -832,7 +887,7 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   launch_kernel(gn_partial_kernel, dim3(stat_blocks), dim3(block), smem_bytes, stream, 1, static_cast<const __half*>(x1), C1,
                                                                 static_cast<const __half*>(x2), C2, HW, pix, n_chunks,
                                                                 n_items, ipc, n_slots, partial, imgsum, counters,
-                                                                frames_per_stat, count, eps, stats);
+                                                                frames_per_stat, count, eps, stats, rev);
   if (int e = check_launch("gn_partial_kernel")) return e;
   // the apply pass may use larger blocks than the statistics pass (its per-block prologue - gamma, beta, statistics -
   // amortises better); SVDPP_GN_APPLY_PIX overrides for experiments
@@ -845,7 +900,8 @@ extern "C" int svdpp_groupnorm_silu(const void* x1, int32_t C1, const void* x2, 
   dim3 grid_apply((HW + apix - 1) / apix, n_img);
   launch_kernel(gn_apply_kernel, dim3(grid_apply), dim3(block), 0, stream, 1, static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2,
                                               static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                              stats, static_cast<__half*>(out), HW, apix, frames_per_stat, apply_silu);
+                                              stats, static_cast<__half*>(out), HW, apix, frames_per_stat, apply_silu,
+                                              rev_apply);
   return check_launch("gn_apply_kernel");
 }
 
@@ -863,14 +919,15 @@ extern "C" int svdpp_layernorm(const void* x, int64_t ldx, const void* addvec, i
   const __half* bh = static_cast<const __half*>(beta);
   __half* oh = static_cast<__half*>(out);
   const int hw = add_hw > 0 ? add_hw : 1, md = add_mod > 0 ? add_mod : 1;
+  const int rev = tuning().reverse == 1 ? 1 : 0;
   if (C == 320)
-    launch_kernel(layernorm_rows_kernel<8>, dim3((M + 31) / 32), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<8>, dim3((M + 31) / 32), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps, rev);
   else if (C == 640)
-    launch_kernel(layernorm_rows_kernel<16>, dim3((M + 15) / 16), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<16>, dim3((M + 15) / 16), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps, rev);
   else if (C == 1280)
-    launch_kernel(layernorm_rows_kernel<32>, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps);
+    launch_kernel(layernorm_rows_kernel<32>, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, eps, rev);
   else
-    launch_kernel(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, C, eps);
+    launch_kernel(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, 1, xh, ldx, ah, hw, md, gh, bh, oh, ldo, M, C, eps, rev);
   return check_launch("layernorm_kernel");
 }
 
@@ -964,17 +1021,43 @@ extern "C" int svdpp_nhwc_to_bfchw(const void* x, void* out, int32_t B, int32_t 
   return check_launch("nhwc_to_bfchw_kernel");
 }
 
-extern "C" int svdpp_euler_vpred_step(const void* latent, const void* v_a, const void* v_cond, const void* gs,
-                                      int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
-                                      int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, svdpp_stream stream_) {
+extern "C" int svdpp_euler_vpred_step_signal(const void* latent, const void* v_a, const void* v_cond, const void* gs,
+                                             int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
+                                             int32_t B, int32_t C, int32_t F, int32_t H, int32_t W,
+                                             const svdpp_handoff* ho, svdpp_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SVDPP_CHECK_ARG(latent && v_a && out, "euler: null pointer");
   SVDPP_CHECK_ARG(v_cond == nullptr || gs != nullptr, "euler: guidance needs gs");
+  SVDPP_CHECK_ARG(ho == nullptr || ho->ready_flag == nullptr || ho->done_counter != nullptr,
+                  "euler: a handoff needs a (zeroed, local) completion counter");
   const long long total = static_cast<long long>(B) * F * H * W;
   launch_kernel(euler_vpred_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 1, 
       static_cast<const __half*>(latent), static_cast<const __half*>(v_a), static_cast<const __half*>(v_cond),
-      static_cast<const __half*>(gs), v_nhwc, c_v, c_x, sigma, dt, static_cast<__half*>(out), B, C, F, H * W);
+      static_cast<const __half*>(gs), v_nhwc, c_v, c_x, sigma, dt, static_cast<__half*>(out), B, C, F, H * W,
+      ho ? static_cast<unsigned*>(ho->done_counter) : nullptr, ho ? static_cast<unsigned*>(ho->ready_flag) : nullptr,
+      ho ? ho->flag_value : 0u);
   return check_launch("euler_vpred_kernel");
+}
+
+extern "C" int svdpp_euler_vpred_step(const void* latent, const void* v_a, const void* v_cond, const void* gs,
+                                      int32_t v_nhwc, float c_v, float c_x, float sigma, float dt, void* out,
+                                      int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, svdpp_stream stream_) {
+  return svdpp_euler_vpred_step_signal(latent, v_a, v_cond, gs, v_nhwc, c_v, c_x, sigma, dt, out, B, C, F, H, W, nullptr,
+                                       stream_);
+}
+
+extern "C" int svdpp_flag_wait(void* flag, uint32_t value, int32_t reset, uint32_t reset_to, int32_t timeout_s,
+                               svdpp_stream stream_) {
+  SVDPP_CHECK_ARG(flag != nullptr, "flag_wait: null flag");
+  const unsigned long long ns = static_cast<unsigned long long>(timeout_s > 0 ? timeout_s : 600) * 1000000000ull;
+  flag_wait_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<unsigned*>(flag), value, reset, reset_to, ns);
+  return check_launch("flag_wait_kernel");
+}
+
+extern "C" int svdpp_flag_set(void* flag, uint32_t value, svdpp_stream stream_) {
+  SVDPP_CHECK_ARG(flag != nullptr, "flag_set: null flag");
+  flag_set_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<unsigned*>(flag), value);
+  return check_launch("flag_set_kernel");
 }
 
 extern "C" int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

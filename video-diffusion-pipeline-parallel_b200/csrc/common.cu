@@ -52,6 +52,10 @@ Tuning& tuning() {
     v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
     e = getenv("SVDPP_FMHA_STAGGER");
     v.fmha_stagger = e != nullptr ? atoi(e) : 0;
+    v.reverse = 0;
+    v.reverse_gn_apply_same = 0;
+    e = getenv("SVDPP_ZIGZAG");
+    v.zigzag = e != nullptr ? atoi(e) : 0;
     return v;
   }();
   return t;
@@ -126,6 +130,9 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "r1_prefetch_max_kb") == 0) return &svdpp::tuning().r1_prefetch_max_kb;
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
+  if (strcmp(key, "reverse") == 0) return &svdpp::tuning().reverse;
+  if (strcmp(key, "reverse_gn_apply_same") == 0) return &svdpp::tuning().reverse_gn_apply_same;
+  if (strcmp(key, "zigzag") == 0) return &svdpp::tuning().zigzag;
   return nullptr;
 }
 

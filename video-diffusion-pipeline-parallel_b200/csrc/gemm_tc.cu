@@ -42,6 +42,7 @@ struct GemmParams {
   long long ldd;
   int n_store;
   int m_tiles, n_tiles;
+  int rev_m;   // walk the M tiles from the last row block to the first (the end of A is hot in L2 after a forward producer)
   int prefetch_r1;  // producer warp pulls the residual tile into L2 one main loop ahead of the epilogue
   // sub-pixel output map (conv mode, up > 1): GEMM row m = pixel (img, h, w) of the cH x cW grid is stored at pixel
   // (up*h + up_y, up*w + up_x) of the (up*cH) x (up*cW) output image
@@ -217,7 +218,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   const int n_items = n_full_items + (tail_w >= 0 ? 1 : 0);
-  auto m_tile_of = [&](int w) { return TWO ? 2 * (w / p.n_tiles) + cta_rank : w / p.n_tiles; };
+  const int m_rows_total = TWO ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  auto m_tile_of = [&](int w) {
+    int r = w / p.n_tiles;
+    if (p.rev_m) r = m_rows_total - 1 - r;
+    return TWO ? 2 * r + cta_rank : r;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -1231,6 +1237,7 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   p.sk_ws_bytes = d->splitk_ws != nullptr ? d->splitk_ws_bytes : 0;
   p.m_tiles = (d->M + 127) / 128;
   p.n_tiles = d->N / BN;
+  p.rev_m = tuning().reverse == 1 ? 1 : 0;
   {
     // measured with the per-thread residual loads: K=320 +20 %, 640 +6 %, 1280 -3 %; with the residual on TMA loads the
     // prefetch no longer pays at K = 640 (0.97x) and costs 1-5 % beyond, so it is kept for K <= 320 only

@@ -189,12 +189,12 @@ class NativeUNet(nn.Module):
         return self._ws
 
     def step_native(self, out, latent, image_latents, uncond_image_latents, enc, ids, gs, *, timestep, in_div, c_v, c_x,
-                    sigma, dt) -> torch.Tensor:
+                    sigma, dt, handoff=None) -> torch.Tensor:
         """One whole denoising step in one C call (``svdpp_unet_step``; reference svd_unet.py:351-439)."""
         B, _, F, H, W = latent.shape
         ws = self._workspace(B, F, H, W)
         self._handle.step(out, latent, image_latents, uncond_image_latents, enc.contiguous(), ids.contiguous(), gs, ws,
-                          timestep=timestep, in_div=in_div, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt)
+                          timestep=timestep, in_div=in_div, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt, handoff=handoff)
         return out
 
     # ------------------------------------------------------------------ weight packing

@@ -195,8 +195,11 @@ class StableVideoUNet(nn.Module):
                              f"but the latent has {F}")
 
     # ------------------------------------------------------------------ one step
-    def _step_native(self, latent: torch.Tensor, step: int) -> torch.Tensor:
-        """pack -> NativeUNet (channels-last, CFG batched) -> CFG + Euler."""
+    def _step_native(self, latent: torch.Tensor, step: int, out: Optional[torch.Tensor] = None, handoff=None
+                     ) -> torch.Tensor:
+        """pack -> NativeUNet (channels-last, CFG batched) -> CFG + Euler.  ``out`` (optional) receives the result - it
+        may be the next stage's peer-mapped receive slot, in which case ``handoff`` makes the Euler kernel raise that
+        stage's flag (distributed/handoff.py)."""
         from .. import native
         B, C, F, H, W = latent.shape
         in_div, c_v, c_x, sigma, dt = sched.step_coefficients(self._sigmas_np, step)
@@ -212,10 +215,10 @@ class StableVideoUNet(nn.Module):
         if hasattr(self.unet, "step_native") and getattr(self.unet, "orchestrator", "") == "c":
             # the whole step behind the C ABI: one svdpp_unet_step call (pack, UNet, guidance + Euler)
             enc, ids, gs = self._cfg_cache if cfg else (self._image_embeddings, self._added_time_ids, None)
-            return self.unet.step_native(torch.empty_like(latent), latent, self._image_latents,
+            return self.unet.step_native(torch.empty_like(latent) if out is None else out, latent, self._image_latents,
                                          self._uncond_image_latents if cfg else None, enc, ids, gs,
                                          timestep=float(self.scheduler_timesteps[step]), in_div=in_div, c_v=c_v, c_x=c_x,
-                                         sigma=sigma, dt=dt)
+                                         sigma=sigma, dt=dt, handoff=handoff)
         x_in = torch.empty((nb * F * H * W, 2 * C), dtype=torch.float16, device=dev)
         if cfg:
             native.pack_unet_input(x_in[:M], latent, strides, C, in_div, self._uncond_image_latents, strides, C,
@@ -229,15 +232,16 @@ class StableVideoUNet(nn.Module):
             enc, ids, gs = self._image_embeddings, self._added_time_ids, None
         t_dev = torch.full((nb,), float(self.scheduler_timesteps[step]), dtype=torch.float32, device=dev)
         v = self.unet.forward_nhwc(x_in, t_dev, enc, ids, nb, F, H, W)
-        out = torch.empty_like(latent)
+        out = torch.empty_like(latent) if out is None else out
         if cfg:
             native.euler_vpred_step(out, latent, v[:M], v_cond=v[M:], gs=gs, v_nhwc=True, c_v=c_v, c_x=c_x,
-                                    sigma=sigma, dt=dt)
+                                    sigma=sigma, dt=dt, handoff=handoff)
         else:
-            native.euler_vpred_step(out, latent, v, v_nhwc=True, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt)
+            native.euler_vpred_step(out, latent, v, v_nhwc=True, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt, handoff=handoff)
         return out
 
-    def _step_foreign(self, latent: torch.Tensor, step: int) -> torch.Tensor:
+    def _step_foreign(self, latent: torch.Tensor, step: int, out: Optional[torch.Tensor] = None, handoff=None
+                      ) -> torch.Tensor:
         """Any other UNet module: call the operator exactly as the reference does (B2)."""
         from .. import native
         B, C, F, H, W = latent.shape
@@ -252,21 +256,23 @@ class StableVideoUNet(nn.Module):
             return self.unet(sample=sample, timestep=timestep, encoder_hidden_states=emb,
                              added_time_ids=self._added_time_ids, return_dict=False)[0].contiguous()
 
-        out = torch.empty_like(latent)
+        out = torch.empty_like(latent) if out is None else out
         if self._cfg_on:
             u = call(self._uncond_image_latents, self._uncond_embeddings)
             c = call(self._image_latents, self._image_embeddings)
             native.euler_vpred_step(out, latent, u, v_cond=c, gs=self._guidance_scale_tensor.reshape(-1).contiguous(),
-                                    v_nhwc=False, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt)
+                                    v_nhwc=False, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt, handoff=handoff)
         else:
             v = call(self._image_latents, self._image_embeddings)
-            native.euler_vpred_step(out, latent, v, v_nhwc=False, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt)
+            native.euler_vpred_step(out, latent, v, v_nhwc=False, c_v=c_v, c_x=c_x, sigma=sigma, dt=dt, handoff=handoff)
         return out
 
-    def _step(self, latent: torch.Tensor, step: int) -> torch.Tensor:
+    supports_peer_out = True      # forward(latent, step, out=..., handoff=...): see distributed/handoff.py
+
+    def _step(self, latent: torch.Tensor, step: int, out: Optional[torch.Tensor] = None, handoff=None) -> torch.Tensor:
         if hasattr(self.unet, "forward_nhwc"):
-            return self._step_native(latent, step)
-        return self._step_foreign(latent, step)
+            return self._step_native(latent, step, out, handoff)
+        return self._step_foreign(latent, step, out, handoff)
 
     @torch.inference_mode()
     def forward_steps(self, latent: torch.Tensor, steps: Sequence[int]) -> torch.Tensor:
@@ -322,8 +328,10 @@ class StableVideoUNet(nn.Module):
         return g_out.clone()
 
     @torch.inference_mode()
-    def forward(self, latent: torch.Tensor, step: int) -> torch.Tensor:
-        """One denoising step with the scheduler update (reference svd_unet.py:351-439)."""
+    def forward(self, latent: torch.Tensor, step: int, out: Optional[torch.Tensor] = None, handoff=None) -> torch.Tensor:
+        """One denoising step with the scheduler update (reference svd_unet.py:351-439).  Extension: ``out`` = tensor
+        that receives the result (e.g. the next pipeline stage's peer-mapped receive slot) and ``handoff`` =
+        ``(done_counter_ptr, ready_flag_ptr, value)`` for the flag the Euler kernel raises once ``out`` is complete."""
         if not self._conditioning_set:
             raise RuntimeError("Conditioning not set. Call set_conditioning() or "
                                "set_dummy_conditioning() before forward().")
@@ -337,12 +345,12 @@ class StableVideoUNet(nn.Module):
             raise ValueError(f"latent must be [B, C, F, H, W], got {tuple(latent.shape)}")
         self._check_conditioning_shapes(latent)
         if not self.use_cuda_graph:
-            return self._step(latent, step)
-        key = (step, tuple(latent.shape))
+            return self._step(latent, step, out, handoff)
+        key = (step, tuple(latent.shape), None if out is None else out.data_ptr(), handoff)
         shape_key = tuple(latent.shape)
         if shape_key not in self._warm:           # first call per shape runs eagerly (fills caches)
             self._warm.add(shape_key)
-            return self._step(latent, step)
+            return self._step(latent, step, out, handoff)
         if key not in self._graphs:
             g_in = latent.clone()
             torch.cuda.synchronize()
@@ -352,7 +360,7 @@ class StableVideoUNet(nn.Module):
             from .. import native
             before = native.LAUNCHES
             with torch.cuda.graph(graph, pool=self._graph_pool):
-                g_out = self._step(g_in, step)
+                g_out = self._step(g_in, step, out, handoff)
             n_kernels = native.LAUNCHES - before
             native.LAUNCHES = before          # capture launches nothing; replays are counted below
             self._graphs[key] = (graph, g_in, g_out, n_kernels)
@@ -361,4 +369,4 @@ class StableVideoUNet(nn.Module):
         graph.replay()
         from .. import native
         native.LAUNCHES += n_kernels
-        return g_out.clone()
+        return g_out.clone() if out is None else out

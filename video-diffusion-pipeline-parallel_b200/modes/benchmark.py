@@ -51,6 +51,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--device", type=str, default="cuda", help="extension: 'cpu' runs the dummy model under gloo")
     p.add_argument("--allow-uneven", action="store_true")
     p.add_argument("--schedule", default="fixed", choices=["fixed", "ring"])
+    p.add_argument("--transport", default="nccl", choices=["nccl", "peer"],
+                   help="extension: 'peer' = peer-mapped receive slots + flags instead of dist.send/recv (CUDA only)")
     return p
 
 
@@ -96,7 +98,7 @@ def main(argv=None) -> dict | None:
     cfg = PipelineConfig(total_steps=args.total_steps, world_size=world, rank=rank,
                          timesteps=list(range(args.total_steps - 1, -1, -1)),   # as the reference (benchmark.py:178)
                          latent_spec=LatentSpec(shape=shape, dtype=dtype, device=device), allow_uneven=args.allow_uneven)
-    stage = PipelineStage(model=model, config=cfg)
+    stage = PipelineStage(model=model, config=cfg, transport=args.transport if on_gpu else "nccl")
 
     def supplier(idx: int) -> torch.Tensor:
         torch.manual_seed(args.seed + idx)

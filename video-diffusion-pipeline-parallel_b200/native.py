@@ -24,8 +24,8 @@ EXPORTED_SYMBOLS = (
     "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_linear_small_grouped",
     "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
-    "svdpp_euler_vpred_step", "svdpp_dummy_unet_step",
-    "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
+    "svdpp_euler_vpred_step", "svdpp_euler_vpred_step_signal", "svdpp_flag_wait", "svdpp_flag_set", "svdpp_dummy_unet_step",
+    "svdpp_unet_step_handoff", "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
     "svdpp_unet_forward", "svdpp_unet_forward_nhwc", "svdpp_unet_step", "svdpp_unet_last_launches", "svdpp_unet_destroy",
 )
 
@@ -84,6 +84,11 @@ class UNetConfig(C.Structure):
         ("eps_transformer", C.c_float), ("eps_out", C.c_float),
         ("gemm_impl", C.c_int32), ("attn_impl", C.c_int32), ("attn_impl_long", C.c_int32),
     ]
+
+
+class Handoff(C.Structure):
+    """``svdpp_handoff``: completion counter (local), ready flag (in the consumer's memory), value to store."""
+    _fields_ = [("done_counter", C.c_void_p), ("ready_flag", C.c_void_p), ("flag_value", C.c_uint32)]
 
 
 class TensorDesc(C.Structure):
@@ -160,6 +165,10 @@ def _bind(lib):
     lib.svdpp_unet_forward_nhwc.argtypes = fwd
     lib.svdpp_unet_step.argtypes = [C.c_void_p] * 7 + [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_size_t,
                                                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.svdpp_unet_step_handoff.argtypes = lib.svdpp_unet_step.argtypes[:-1] + [C.POINTER(Handoff), C.c_void_p]
+    lib.svdpp_euler_vpred_step_signal.argtypes = lib.svdpp_euler_vpred_step.argtypes[:-1] + [C.POINTER(Handoff), C.c_void_p]
+    lib.svdpp_flag_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]
+    lib.svdpp_flag_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     lib.svdpp_unet_last_launches.restype = C.c_longlong
     lib.svdpp_unet_last_launches.argtypes = [C.c_void_p]
     lib.svdpp_unet_destroy.restype = None
@@ -481,15 +490,41 @@ def nhwc_to_bfchw(out, x, *, B, F, Cc, H, W) -> torch.Tensor:
     return out
 
 
+def make_handoff(handoff) -> Optional["Handoff"]:
+    """(done_counter_ptr, ready_flag_ptr, value) -> svdpp_handoff, or None."""
+    if handoff is None:
+        return None
+    h = Handoff()
+    h.done_counter, h.ready_flag, h.flag_value = int(handoff[0]), int(handoff[1]), int(handoff[2])
+    return h
+
+
 def euler_vpred_step(out, latent, v_a, *, v_cond=None, gs=None, v_nhwc: bool, c_v: float, c_x: float,
-                     sigma: float, dt: float) -> torch.Tensor:
+                     sigma: float, dt: float, handoff=None) -> torch.Tensor:
+    """``handoff=(done_counter_ptr, ready_flag_ptr, value)``: ``out`` is a peer-mapped receive slot and the kernel
+    raises the consumer's flag when its stores are complete (svdpp_euler_vpred_step_signal)."""
     _req(out), _req(latent), _req(v_a)
     B, Cc, F, H, W = latent.shape
-    _check(load().svdpp_euler_vpred_step(latent.data_ptr(), v_a.data_ptr(), _ptr(v_cond), _ptr(gs),
-                                         1 if v_nhwc else 0, c_v, c_x, sigma, dt, out.data_ptr(), B, Cc, F, H, W,
-                                         _stream()), "svdpp_euler_vpred_step")
+    h = make_handoff(handoff)
+    _check(load().svdpp_euler_vpred_step_signal(latent.data_ptr(), v_a.data_ptr(), _ptr(v_cond), _ptr(gs),
+                                                1 if v_nhwc else 0, c_v, c_x, sigma, dt, out.data_ptr(), B, Cc, F, H, W,
+                                                C.byref(h) if h is not None else None, _stream()),
+           "svdpp_euler_vpred_step")
     _count(1)
     return out
+
+
+def flag_wait(flag_ptr: int, value: int, *, reset_to: Optional[int] = None, timeout_s: int = 600) -> None:
+    """Stream-ordered wait until the uint32 at ``flag_ptr`` (written by a peer GPU) equals ``value``."""
+    _check(load().svdpp_flag_wait(flag_ptr, value, 0 if reset_to is None else 1, 0 if reset_to is None else reset_to,
+                                  timeout_s, _stream()), "svdpp_flag_wait")
+    _count(1)
+
+
+def flag_set(flag_ptr: int, value: int) -> None:
+    """Stream-ordered release store of ``value`` to the uint32 at ``flag_ptr`` (possibly peer-mapped)."""
+    _check(load().svdpp_flag_set(flag_ptr, value, _stream()), "svdpp_flag_set")
+    _count(1)
 
 
 def dummy_unet_step(out, x, w1, b1, w2, b2, ln_g, ln_b, ln_eps, tanh_scale, hidden_ws) -> torch.Tensor:
@@ -585,11 +620,13 @@ class UNetHandle:
                       ws.data_ptr(), ws.numel() * ws.element_size(), B, F, H, W, _stream()), "svdpp_unet_forward")
 
     def step(self, out, latent, image_latents, uncond_image_latents, enc, ids, gs, ws, *, timestep, in_div, c_v, c_x,
-             sigma, dt) -> None:
+             sigma, dt, handoff=None) -> None:
         for t in (out, latent, image_latents, enc, ids):
             _req(t)
         B, _, F, H, W = latent.shape
-        self._done(self._lib.svdpp_unet_step(self._h, latent.data_ptr(), image_latents.data_ptr(),
-                                             _ptr(uncond_image_latents), enc.data_ptr(), ids.data_ptr(), _ptr(gs),
-                                             float(timestep), in_div, c_v, c_x, sigma, dt, out.data_ptr(), ws.data_ptr(),
-                                             ws.numel() * ws.element_size(), B, F, H, W, _stream()), "svdpp_unet_step")
+        h = make_handoff(handoff)
+        self._done(self._lib.svdpp_unet_step_handoff(self._h, latent.data_ptr(), image_latents.data_ptr(),
+                                                     _ptr(uncond_image_latents), enc.data_ptr(), ids.data_ptr(), _ptr(gs),
+                                                     float(timestep), in_div, c_v, c_x, sigma, dt, out.data_ptr(),
+                                                     ws.data_ptr(), ws.numel() * ws.element_size(), B, F, H, W,
+                                                     C.byref(h) if h is not None else None, _stream()), "svdpp_unet_step")

@@ -14,7 +14,11 @@ What differs from the reference is *how* the handoff is issued, not what is exch
   deliberately not left pending across compute: an NCCL send/recv kernel that spins for its peer occupies
   SMs, and the persistent one-CTA-per-SM kernels of this path would then run a whole extra wave.  The
   1.8 MB latent costs microseconds on NVLink against >= 100 ms of compute per stage and video;
-* ``PipelineConfig.allow_uneven`` opts into ``assign_steps_uneven`` (the reference raises, Q1).
+* ``PipelineConfig.allow_uneven`` opts into ``assign_steps_uneven`` (the reference raises, Q1);
+* ``PipelineStage(..., transport="peer")`` (or ``PIPELINE_TRANSPORT=peer``) replaces the NCCL send/recv by the
+  peer-mapped, flag-signalled handoff of ``distributed/handoff.py``: the producer's last local step writes the latent
+  straight into the next stage's receive slot over NVLink and raises its flag from the same kernel; ranks are no
+  longer coupled by collective-style exchanges (CUDA devices only).
 
 Message order, tags, shapes and the values exchanged are identical, so a mixed world of reference
 and new stages interoperates.
@@ -22,6 +26,7 @@ and new stages interoperates.
 from __future__ import annotations
 
 import logging
+import os
 import time
 from collections.abc import Sequence
 from dataclasses import dataclass
@@ -68,10 +73,15 @@ InputSupplier = Callable[[int], torch.Tensor]
 class PipelineStage:
     """One rank of the step pipeline."""
 
-    def __init__(self, model, config: PipelineConfig, logger: Optional[logging.Logger] = None) -> None:
+    def __init__(self, model, config: PipelineConfig, logger: Optional[logging.Logger] = None,
+                 transport: Optional[str] = None) -> None:
         self.model = model
         self.config = config
         self.logger = logger or LOGGER
+        self.transport = (transport or os.environ.get("PIPELINE_TRANSPORT", "nccl")).lower()
+        if self.transport not in ("nccl", "peer"):
+            raise ValueError("transport must be 'nccl' (dist.send / dist.recv) or 'peer' (peer-mapped slots + flags)")
+        self._peer = None
         split = assign_steps_uneven if config.allow_uneven else assign_steps
         self.step_range: StepRange = split(
             total_steps=config.total_steps, world_size=config.world_size, rank=config.rank
@@ -126,6 +136,30 @@ class PipelineStage:
             work = dist.isend(latent, dst=self.config.rank + 1, tag=self.config.send_tag)
             self._pending_send = (work, latent)
 
+    # ------------------------------------------------------------------ peer-mapped transport
+    def _peer_handoff(self):
+        if self._peer is None:
+            from ..distributed.handoff import PeerHandoff
+            spec = self.config.latent_spec
+            self._peer = PeerHandoff(spec.shape, spec.dtype, spec.device)
+        return self._peer
+
+    def _run_steps_and_hand_over(self, latent: torch.Tensor, steps: Sequence[int]) -> None:
+        """The slice ``steps`` on ``latent``, its LAST step writing straight into the next rank's receive slot and
+        raising that rank's flag (models with ``supports_peer_out``); other models run normally and the result is
+        copied over.  Replaces ``_run_steps`` + ``_send_latent`` when ``transport == "peer"``."""
+        peer = self._peer_handoff()
+        steps = list(steps)
+        if steps and getattr(self.model, "supports_peer_out", False):
+            if len(steps) > 1:
+                latent = self._run_steps(latent, steps[:-1])
+            slot, handoff = peer.begin_send()
+            self.model(latent, steps[-1], out=slot, handoff=handoff)
+            return
+        if steps:
+            latent = self._run_steps(latent, steps)
+        peer.send_copy(latent)
+
     # ------------------------------------------------------------------ compute
     def _run_local_steps(self, latent: torch.Tensor) -> torch.Tensor:
         """The inner hot loop (reference ``pipeline.py:86-98``): ``model(latent, timesteps[i])``."""
@@ -166,12 +200,17 @@ class PipelineStage:
                 if latent is None:
                     raise ValueError("rank 0 requires an input latent tensor")
                 latent = latent.to(cfg.latent_spec.device)
+            elif self.transport == "peer":
+                latent = self._peer_handoff().recv()
             else:
                 work, buf = self._post_recv()
                 work.wait()
                 # the slot is rewritten two samples later; the model returns a fresh tensor per step,
                 # but an empty stage would forward the slot itself, hence the clone there
                 latent = buf if self.step_range.count else buf.clone()
+            if self.transport == "peer" and not last:
+                self._run_steps_and_hand_over(latent, self._local_timesteps)
+                continue
             latent = self._run_local_steps(latent)
             if last:
                 outputs.append(latent)
@@ -215,6 +254,14 @@ class PipelineStage:
                     if cur is None:
                         raise ValueError("input_supplier returned None")
                     cur = cur.to(cfg.latent_spec.device)
+                if self.transport == "peer" and t < W - 1:
+                    # no collective-style exchange: my video's last step of this stage lands in the next rank's slot and
+                    # raises its flag; I wait for nothing but the one latent I need next
+                    if exists:
+                        self._run_steps_and_hand_over(cur, cfg.timesteps[stages[t].start: stages[t].end])
+                    v_in = b * W + (r - 1 - t) % W
+                    cur = self._peer_handoff().recv() if v_in < num_samples else None
+                    continue
                 if exists:
                     cur = self._run_steps(cur, cfg.timesteps[stages[t].start: stages[t].end])
                 if t == W - 1:
@@ -251,9 +298,12 @@ class PipelineStage:
         else:
             if input_latent is not None:
                 raise ValueError("non-zero ranks should not receive an eager latent")
-            latent = self._recv_latent()
+            latent = self._peer_handoff().recv() if self.transport == "peer" else self._recv_latent()
             self._log(f"{prefix}received latent")
 
+        if self.transport == "peer" and cfg.rank != cfg.world_size - 1:
+            self._run_steps_and_hand_over(latent, self._local_timesteps)
+            return None
         latent = self._run_local_steps(latent)
 
         if cfg.rank == cfg.world_size - 1:
