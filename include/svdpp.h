@@ -43,6 +43,13 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *                   ("splitk_min_kb": fewest 64-wide k-blocks a slice may get, default 4; "splitk_min_total_kb": only for
  *                   K / 64 >= this, default 64)
  *   "r1_prefetch_max_kb"  the GEMM producer warp prefetches the residual tile into L2 for K / 64 <= this (default 5; 0: never)
+ *   "fmha_stagger"  SM clocks by which the second query tile of the two-tile FMHA starts behind the first (default 900; SVDPP_FMHA_STAGGER)
+ *   "reverse"    traversal direction of the NEXT GEMM / LayerNorm / GroupNorm launches: 1 = from the last rows to the first (the end
+ *                   of a tensor a forward producer has just written is still in L2); GroupNorm: 1 = statistics from the end / apply
+ *                   forward, 2 = statistics forward / apply from the end; 0 (default) = forward.  A GEMM whose last wave is split
+ *                   along K keeps the forward order.
+ *   "zigzag"     1: svdpp_unet_* flip that direction from producer to consumer along the network (default 0: measured -0.4 ms
+ *                   of 93.9 ms per step, inside the noise; SVDPP_ZIGZAG)
  *   "pdl"        1: kernels are launched with programmatic stream serialisation (the prologue of kernel N+1
  *                   overlaps the tail of kernel N; every kernel waits on griddepcontrol before touching memory)
  * set returns 0, or -1 for an unknown key; get returns the value, or -1 for an unknown key.
@@ -233,6 +240,22 @@ int svdpp_euler_vpred_step_signal(const void* latent, const void* v_a, const voi
                                   svdpp_stream stream);
 int svdpp_flag_wait(void* flag, uint32_t value, int32_t reset, uint32_t reset_to, int32_t timeout_s, svdpp_stream stream);
 int svdpp_flag_set(void* flag, uint32_t value, svdpp_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * VAE front / back end (AutoencoderKLTemporalDecoder; reference scripts/generate_video_demo.py:119-143 encode, :154-195
+ * decode).  Its convolutions and linears are svdpp_gemm_f16 calls; these are the pieces in between.
+ * -------------------------------------------------------------------------------------------*/
+/* In-place softmax over each row of an fp16 matrix [rows, n] (row pitch ld): x <- softmax(scale * x), fp32 maths; columns
+ * >= n_valid (0: all n) are padding keys: ignored and written as 0.  The single-head, head_dim-512 attention of the VAE mid
+ * blocks and the 257-token attention of the CLIP image encoder = GEMM (Q K^T) -> this -> GEMM (P V). */
+int svdpp_softmax_rows(void* x, int64_t ld, int32_t rows, int32_t n, int32_t n_valid, float scale, svdpp_stream stream);
+/* out[c, r] = in[r, c] for an fp16 matrix [R, C] (V -> V^T, the K-major B operand of the P V product). */
+int svdpp_transpose_f16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t R, int32_t C, svdpp_stream stream);
+/* TemporalDecoder.time_conv_out: Conv3d (3,1,1) over the frames of a 3-channel video, reading the channels-last output of
+ * conv_out [B, F, HW, x_channels >= 3] (the first 3 channels; conv_out is stored 4 wide so that its rows are 8-byte
+ * aligned) and writing the caller's [B*F, 3, HW] (fp32 if out_fp32 else fp16).  w is [3, 3, 3] = (co, ci, kt). */
+int svdpp_time_conv_out(const void* x, int32_t x_channels, const void* w, const void* bias, void* out, int32_t out_fp32,
+                        int32_t B, int32_t F, int64_t HW, svdpp_stream stream);
 
 /* DummyUNet step (reference src/models/dummy_unet.py:37-59), fp32, [B, C, F, H, W]:
  *   out = x + tanh_scale * conv3d(silu(conv3d(x, w1, b1)), w2, b2) + layernorm_C(x) */

@@ -381,6 +381,111 @@ def handoff_flags(cfg=True):
     return dict(max_err=0.0 if ok else 1.0, tol=0.0, ok=bool(ok))
 
 
+def softmax_rows(rows=70, n=384, scale=0.3):
+    x = (_rand(rows, n + 8, seed=1).float() * 6).half()
+    got = x.clone()
+    native.softmax_rows(got[:, :n], scale)
+    ref = torch.softmax(x[:, :n].float() * scale, dim=-1)
+    torch.cuda.synchronize()
+    r = _cmp(got[:, :n], ref, rel=2e-3, floor=1e-5)
+    r["ok"] = bool(r["ok"] and torch.equal(got[:, n:], x[:, n:]))          # columns beyond n (the row pitch) untouched
+    return r
+
+
+def transpose(R=300, C=520):
+    x = _rand(R, C + 8, seed=1)[:, :C]
+    out = torch.full((C, R + 8), float("nan"), device=DEV, dtype=torch.float16)
+    native.transpose(out[:, :R], x)
+    torch.cuda.synchronize()
+    ok = torch.equal(out[:, :R], x.t()) and bool(torch.isnan(out[:, R:]).all())
+    return dict(max_err=0.0 if ok else 1.0, tol=0.0, ok=bool(ok))
+
+
+def time_conv_out(B=2, Fr=5, H=6, W=10, fp32=True):
+    x = _rand(B * Fr * H * W, 4, seed=1)
+    w, b = _rand(3, 3, 3, seed=2), _rand(3, seed=3)
+    out = torch.full((B * Fr, 3, H, W), float("nan"), device=DEV, dtype=torch.float32 if fp32 else torch.float16)
+    native.time_conv_out(out, x, w, b, B=B, F=Fr, HW=H * W)
+    x5 = x[:, :3].float().reshape(B, Fr, H, W, 3).permute(0, 4, 1, 2, 3)                 # [B, 3, F, H, W]
+    ref = F.conv3d(x5, w.float()[:, :, :, None, None], b.float(), padding=(1, 0, 0))
+    ref = ref.permute(0, 2, 1, 3, 4).reshape(B * Fr, 3, H, W)
+    torch.cuda.synchronize()
+    return _cmp(out, ref, rel=2e-3, floor=2e-3)
+
+
+def _tiny_vae(seed=0, **over):
+    from oracle.vae_torch import AutoencoderKLTemporalDecoder, tiny_vae_config
+    from vdpp_b200.models.native_vae import NativeVAE
+    torch.manual_seed(seed)
+    cfg = tiny_vae_config(**over)
+    oracle = AutoencoderKLTemporalDecoder(**cfg).to(DEV).eval()
+    with torch.no_grad():                       # non-trivial norms / blends so that every path shows up in the output
+        for n_, p_ in oracle.named_parameters():
+            if n_.endswith("mix_factor"):
+                p_.fill_(0.3)
+            elif "norm" in n_ and n_.endswith("weight"):
+                p_.add_(0.2 * torch.randn_like(p_))
+            elif "norm" in n_ and n_.endswith("bias"):
+                p_.add_(0.1 * torch.randn_like(p_))
+    oracle = oracle.half()                      # fp16-representable weights on both sides
+    nat = NativeVAE(oracle.state_dict(), config=cfg, device=DEV)
+    return oracle, nat
+
+
+def vae_decode(B=1, Fr=3, h=8, w=16, **over):
+    """NativeVAE.decode vs the torch restatement of AutoencoderKLTemporalDecoder in fp32 on the same (fp16) weights."""
+    oracle, nat = _tiny_vae(**over)
+    z = (_rand(B * Fr, 4, h, w, seed=5).float() * 3).half()
+    got = nat.decode(z, num_frames=Fr, out_dtype=torch.float32).sample
+    with torch.no_grad():
+        ref32 = oracle.float().decode(z.float(), num_frames=Fr).sample
+        ref16 = oracle.half().decode(z, num_frames=Fr).sample
+    torch.cuda.synchronize()
+    r = _cmp(got, ref32, rel=2e-2, floor=2e-3)
+    floor16 = (ref16.float() - ref32).abs().max().item()
+    r["lib_fp16_vs_fp32"] = floor16
+    r["ok"] = bool(r["ok"] and r["max_err"] <= max(4 * floor16, 5e-3) and tuple(got.shape) == (B * Fr, 3, 8 * h, 8 * w))
+    return r
+
+
+def vae_encode(N=2, H=64, W=128, **over):
+    oracle, nat = _tiny_vae(**over)
+    x = (_rand(N, 3, H, W, seed=6).float().clamp(-1, 1)).half()
+    got = nat.encode(x).latent_dist.mode()
+    with torch.no_grad():
+        ref32 = oracle.float().encode(x.float()).latent_dist.mode()
+        ref16 = oracle.half().encode(x).latent_dist.mode()
+    torch.cuda.synchronize()
+    r = _cmp(got, ref32, rel=2e-2, floor=2e-3)
+    floor16 = (ref16.float() - ref32).abs().max().item()
+    r["lib_fp16_vs_fp32"] = floor16
+    r["ok"] = bool(r["ok"] and r["max_err"] <= max(4 * floor16, 5e-3) and tuple(got.shape) == tuple(ref32.shape))
+    return r
+
+
+def clip_vision(B=2, **over):
+    """NativeCLIPVision vs the REAL transformers CLIPVisionModelWithProjection on the same weights (fp32 and fp16)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    from vdpp_b200.models.native_clip import NativeCLIPVision
+    cfg = dict(hidden_size=192, intermediate_size=384, num_hidden_layers=2, num_attention_heads=4, image_size=56,
+               patch_size=14, projection_dim=64, hidden_act="gelu")
+    cfg.update(over)
+    torch.manual_seed(0)
+    lib = CLIPVisionModelWithProjection(CLIPVisionConfig(**cfg)).to(DEV).half().eval()
+    nat = NativeCLIPVision(lib.state_dict(), config=cfg, device=DEV)
+    px = _rand(B, 3, cfg["image_size"], cfg["image_size"], seed=3)
+    got = nat(px).image_embeds
+    with torch.no_grad():
+        ref16 = lib(pixel_values=px).image_embeds
+        ref32 = lib.float()(pixel_values=px.float()).image_embeds
+    torch.cuda.synchronize()
+    r = _cmp(got, ref32, rel=1e-2, floor=2e-3)
+    floor16 = (ref16.float() - ref32).abs().max().item()
+    r["lib_fp16_vs_fp32"] = floor16
+    r["ok"] = bool(r["ok"] and r["max_err"] <= max(4 * floor16, 3e-3) and tuple(got.shape) == tuple(ref32.shape))
+    return r
+
+
 def dummy_unet(C=4, Ch=16, step=7):
     from vdpp_b200.models import DummyUNet
     torch.manual_seed(0)
@@ -410,6 +515,12 @@ ALL_CHECKS = {
     "layernorm_1280": lambda: layernorm(M=33, C=1280, add=False),
     "layernorm_640": lambda: layernorm(M=37, C=640, add=True),
     "layernorm_generic": lambda: layernorm(M=19, C=128, add=True),
+    "softmax_rows": lambda: softmax_rows(),
+    "softmax_rows_9216": lambda: softmax_rows(rows=33, n=9216, scale=512 ** -0.5),
+    "transpose": lambda: transpose(),
+    "transpose_9216x512": lambda: transpose(R=9216, C=512),
+    "time_conv_out_fp32": lambda: time_conv_out(fp32=True),
+    "time_conv_out_fp16": lambda: time_conv_out(B=1, Fr=1, fp32=False),
     "handoff_flags_cfg": lambda: handoff_flags(True),
     "handoff_flags_nocfg": lambda: handoff_flags(False),
     "groupnorm": lambda: groupnorm(),
@@ -710,6 +821,14 @@ UNET_CHECKS = {
     "svd_steps_tc_cfg_pyorch": lambda: svd_steps(cfg_scale=3.0, orchestrator="python"),
     "svd_steps_tc_graph_pyorch": lambda: svd_steps(graph=True, orchestrator="python"),
 }
+UNET_CHECKS["clip_vision_tiny"] = lambda: clip_vision()
+UNET_CHECKS["clip_vision_hd80"] = lambda: clip_vision(B=1, hidden_size=320, num_attention_heads=4, intermediate_size=1280,
+                                                      num_hidden_layers=3, image_size=224, projection_dim=128)
+UNET_CHECKS["vae_decode_tiny"] = lambda: vae_decode()
+UNET_CHECKS["vae_decode_tiny_b2"] = lambda: vae_decode(B=2, Fr=2, h=16, w=8)
+UNET_CHECKS["vae_decode_3level"] = lambda: vae_decode(B=1, Fr=2, h=8, w=16, block_out_channels=(64, 128, 256), layers_per_block=2)
+UNET_CHECKS["vae_encode_tiny"] = lambda: vae_encode()
+UNET_CHECKS["vae_encode_3level"] = lambda: vae_encode(N=1, H=128, W=128, block_out_channels=(64, 128, 256))
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
 UNET_CHECKS["unet_tiny_tc_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_tc"], zigzag=1)      # producer -> consumer direction flips
 UNET_CHECKS["unet_tiny_pair256_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], zigzag=1)

@@ -1173,6 +1173,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
         if (S >= 2 && 4096 + static_cast<long long>(r) * S * part_bytes <= p.sk_ws_bytes &&
             static_cast<size_t>(r) * 4 * sizeof(unsigned) <= 4096) {
           p.splitk = S;
+          // which tiles land in the split last wave depends on the walk order, and a split tile sums its k-slices in
+          // another association than an unsplit one: keep the forward walk so results do not depend on "reverse"
+          p.rev_m = 0;
           p.sk_r = r;
           p.sk_full = full_waves * clusters;
           p.sk_cnt = reinterpret_cast<unsigned*>(p.sk_ws);

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
     "svdpp_euler_vpred_step", "svdpp_euler_vpred_step_signal", "svdpp_flag_wait", "svdpp_flag_set", "svdpp_dummy_unet_step",
+    "svdpp_softmax_rows", "svdpp_transpose_f16", "svdpp_time_conv_out",
     "svdpp_unet_step_handoff", "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
     "svdpp_unet_forward", "svdpp_unet_forward_nhwc", "svdpp_unet_step", "svdpp_unet_last_launches", "svdpp_unet_destroy",
 )
@@ -169,6 +170,10 @@ def _bind(lib):
     lib.svdpp_euler_vpred_step_signal.argtypes = lib.svdpp_euler_vpred_step.argtypes[:-1] + [C.POINTER(Handoff), C.c_void_p]
     lib.svdpp_flag_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]
     lib.svdpp_flag_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.svdpp_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    lib.svdpp_transpose_f16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_time_conv_out.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int64, C.c_void_p]
     lib.svdpp_unet_last_launches.restype = C.c_longlong
     lib.svdpp_unet_last_launches.argtypes = [C.c_void_p]
     lib.svdpp_unet_destroy.restype = None
@@ -510,6 +515,37 @@ def euler_vpred_step(out, latent, v_a, *, v_cond=None, gs=None, v_nhwc: bool, c_
                                                 1 if v_nhwc else 0, c_v, c_x, sigma, dt, out.data_ptr(), B, Cc, F, H, W,
                                                 C.byref(h) if h is not None else None, _stream()),
            "svdpp_euler_vpred_step")
+    _count(1)
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, n_valid: int = 0) -> torch.Tensor:
+    """In-place ``softmax(scale * x, dim=-1)`` of an fp16 matrix (row pitch may exceed the row length); columns
+    ``>= n_valid`` (0: none) are padding keys and come out as 0."""
+    _req(x)
+    _check(load().svdpp_softmax_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], n_valid, scale, _stream()),
+           "svdpp_softmax_rows")
+    _count(1)
+    return x
+
+
+def transpose(out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """out [C, R] <- x [R, C] (fp16, row pitches taken from the tensors)."""
+    _req(out), _req(x)
+    _check(load().svdpp_transpose_f16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                      _stream()), "svdpp_transpose_f16")
+    _count(1)
+    return out
+
+
+def time_conv_out(out: torch.Tensor, x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, B: int, F: int, HW: int
+                  ) -> torch.Tensor:
+    """TemporalDecoder.time_conv_out: x channels-last [B*F*HW, >= 3] fp16 -> out [B*F, 3, H, W] (fp16 or fp32)."""
+    _req(x), _req(w), _req(bias)
+    if out.dtype not in (torch.float16, torch.float32) or not out.is_cuda:
+        raise NativeError("time_conv_out: out must be a CUDA fp16 / fp32 tensor")
+    _check(load().svdpp_time_conv_out(x.data_ptr(), x.shape[1], w.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                      1 if out.dtype == torch.float32 else 0, B, F, HW, _stream()), "svdpp_time_conv_out")
     _count(1)
     return out
 
