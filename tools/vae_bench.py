@@ -67,7 +67,7 @@ def main():
         # the reference's path: fp32 VAE (force_upcast), torch library kernels, same chunking
         lib32 = lib.float()
         t0 = time.time()
-        ms_lib, frames_lib = timed(lambda: decode_latents(lat, lib32, a.frames, a.chunk), n=1)
+        ms_lib, frames_lib = timed(lambda: decode_latents(lat.float(), lib32, a.frames, a.chunk), n=1)
         res["decode_library_fp32_ms"] = ms_lib
         res["decode_native_vs_library_fp32"] = diff(frames, frames_lib)
         ms_lib, z_lib = timed(lambda: lib32.encode(img.float()).latent_dist.mode(), n=1)
