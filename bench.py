@@ -58,9 +58,10 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true",
                    help="enqueue every launch eagerly instead of replaying one CUDA graph per denoising step (within "
                         "+-1 %%: the host runs ~740 launches per step ahead of the GPU either way)")
-    p.add_argument("--transport", default="nccl", choices=["nccl", "peer"],
-                   help="N>1 latent handoff: 'nccl' = dist.send/recv (isend/irecv waited on the stream), 'peer' = the next "
-                        "stage's peer-mapped receive slot written by the producer's Euler kernel + flag (distributed/handoff.py)")
+    p.add_argument("--transport", default="peer", choices=["nccl", "peer"],
+                   help="N>1 latent handoff: 'peer' (default) = the next stage's peer-mapped receive slot written by the "
+                        "producer's Euler kernel + flag (distributed/handoff.py; falls back to nccl on every rank if the "
+                        "symmetric-memory rendezvous fails anywhere), 'nccl' = dist.send/recv waited on the stream")
     p.add_argument("--force-graph", action="store_true", help="N=1: skip the eager-vs-graph measurement, use graphs")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-library-baseline", action="store_true")
@@ -337,6 +338,19 @@ def main() -> None:
     cfg = PipelineConfig(total_steps=T, world_size=world, rank=rank, timesteps=list(range(T)), latent_spec=spec,
                          allow_uneven=True)
     stage = PipelineStage(model=model, config=cfg, transport=args.transport if world > 1 else "nccl")
+    transport_note = None
+    if world > 1 and stage.transport == "peer":
+        # the peer-mapped slots need a symmetric-memory rendezvous; if it fails on ANY rank, every rank uses NCCL
+        try:
+            stage._peer_handoff()
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            ok, transport_note = 0, f"peer handoff unavailable on rank {rank}: {type(e).__name__}: {e}"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            stage.transport, stage._peer = "nccl", None
+            transport_note = transport_note or "peer handoff unavailable on another rank"
     n_videos = K * world
     last = rank == world - 1
 
@@ -557,6 +571,9 @@ def main() -> None:
         }
         if launch_mode is not None:
             result["launch_mode"] = launch_mode
+        if world > 1:
+            result["handoff"] = {"transport": stage.transport, "note": transport_note,
+                                 "bytes_per_boundary_per_video": bytes_lat}
         if placements is not None:
             result["placements"] = placements
             result["linear_pipeline"] = {"value": placements["fixed"]["steady_videos_per_min"], "unit": UNIT,
