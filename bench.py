@@ -633,7 +633,7 @@ def main() -> None:
         att = agg.get("attn_spatial")
         if att:
             result["roofline_attention"] = {
-                "kernel": "attn_spatial2_tc_kernel / attn_spatial_tc_kernel (tcgen05 FMHA)", "bound": "tensor",
+                "kernel": "attn_spatial3_tc_kernel (S >= 1024, ping-pong) / attn_spatial_tc_kernel (tcgen05 FMHA)", "bound": "tensor",
                 "achieved": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
                 "frac": fl["attn_spatial"] / (att[0] / 1000.0) / 1e12 / peak, "launches": att[2], "ms": att[0],
                 # head_dim 64: one MUFU.EX2 per score (16/clk/SM, tools/ubench) against 256 tensor FLOP per score

@@ -505,6 +505,19 @@ def dummy_unet(C=4, Ch=16, step=7):
     return _cmp(out, ref, rel=1e-4, floor=1e-4)
 
 
+def _tuned_later(fn_name, kw, **switches):
+    """A check that runs globals()[fn_name](**kw) with tuning switches set (restored afterwards)."""
+    def run():
+        old = {k: native.set_tuning(k, v) for k, v in switches.items()}
+        try:
+            return globals()[fn_name](**kw)
+        finally:
+            torch.cuda.synchronize()
+            for k, v in old.items():
+                native.set_tuning(k, v)
+    return run
+
+
 ALL_CHECKS = {
     "movers": lambda: movers(),
     "euler_cfg": lambda: euler(True),
@@ -624,6 +637,15 @@ ALL_CHECKS = {
                      ("144", dict(n_img=3, S=144, heads=2)), ("576", dict(n_img=2, S=576, heads=3)),
                      ("2304", dict(n_img=2, S=2304, heads=5)), ("rescale", dict(n_img=2, S=1000, heads=2, growing=True)),
                      ("rescale_late", dict(n_img=1, S=1200, heads=1, growing="late")))},
+    # ping-pong kernel (impl 7, fmha3_tc.cu): the two tiles' exponential phases alternate through named barriers
+    **{f"tc7_attn_spatial_{n}": (lambda kw=kw: attn_spatial(impl=7, **kw))
+       for n, kw in (("64", dict(n_img=2, S=64, heads=1)), ("256", dict(n_img=1, S=256, heads=1)),
+                     ("tail", dict(n_img=2, S=320, heads=2)), ("144", dict(n_img=3, S=144, heads=2)),
+                     ("576", dict(n_img=2, S=576, heads=3)), ("2304", dict(n_img=2, S=2304, heads=5)),
+                     ("rescale", dict(n_img=2, S=1000, heads=2, growing=True)),
+                     ("rescale_late", dict(n_img=1, S=1200, heads=1, growing="late")))},
+    **{f"tc7_attn_spatial_handover{h}": _tuned_later("attn_spatial", dict(impl=7, n_img=2, S=1000, heads=2, growing=True), fmha_handover=h)
+       for h in (0, 7)},
 }
 
 

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--impls", default="2,4,5,6")
 ap.add_argument("--staggers", default="0,300,600,900,1200")
 ap.add_argument("--iters", type=int, default=6)
+ap.add_argument("--key", default="fmha_stagger", help="tuning key the --staggers values are written to (fmha_stagger | fmha_handover)")
 ap.add_argument("--out", default="attn_sweep.json")
 a = ap.parse_args()
 impls = [int(x) for x in a.impls.split(",")]
@@ -36,7 +37,7 @@ for S, heads, imgs in shapes:
     fl = 4.0 * S * S * 64 * heads * imgs
     for impl in impls:
         for st in staggers:
-            native.set_tuning("fmha_stagger", st)
+            native.set_tuning(a.key, st)
             out = torch.empty_like(ref)
             ts = []
             for i in range(a.iters + 2):
@@ -49,11 +50,12 @@ for S, heads, imgs in shapes:
                 if i >= 2:
                     ts.append(e0.elapsed_time(e1))
             err = (out.float() - ref.float()).abs().max().item()
-            row = dict(S=S, heads=heads, imgs=imgs, impl=impl, stagger=st, best_ms=min(ts), median_ms=statistics.median(ts),
+            row = dict(S=S, heads=heads, imgs=imgs, impl=impl, key=a.key, stagger=st, best_ms=min(ts), median_ms=statistics.median(ts),
                        tflops_best=fl / min(ts) / 1e9, tflops_median=fl / statistics.median(ts) / 1e9,
                        max_abs_vs_impl2=err, finite=bool(torch.isfinite(out).all()))
             res.append(row)
             print(json.dumps(row), flush=True)
-native.set_tuning("fmha_stagger", 0)
+native.set_tuning("fmha_stagger", 900)
+native.set_tuning("fmha_handover", 2)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", a.out), "w"), indent=1)

@@ -52,6 +52,8 @@ Tuning& tuning() {
     v.epi_dma_max_kb = e != nullptr ? atoi(e) : 5;
     e = getenv("SVDPP_FMHA_STAGGER");
     v.fmha_stagger = e != nullptr ? atoi(e) : 900;   // in-situ A/B (profiles/r2_ab_attn_insitu.json): 94.8 -> 92.9 ms per step with impl 4
+    e = getenv("SVDPP_FMHA_HANDOVER");
+    v.fmha_handover = e != nullptr ? atoi(e) : 2;
     v.reverse = 0;
     v.reverse_gn_apply_same = 0;
     e = getenv("SVDPP_ZIGZAG");
@@ -130,6 +132,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "r1_prefetch_max_kb") == 0) return &svdpp::tuning().r1_prefetch_max_kb;
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
+  if (strcmp(key, "fmha_handover") == 0) return &svdpp::tuning().fmha_handover;
   if (strcmp(key, "reverse") == 0) return &svdpp::tuning().reverse;
   if (strcmp(key, "reverse_gn_apply_same") == 0) return &svdpp::tuning().reverse_gn_apply_same;
   if (strcmp(key, "zigzag") == 0) return &svdpp::tuning().zigzag;

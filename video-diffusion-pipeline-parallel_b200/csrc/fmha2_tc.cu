@@ -32,7 +32,7 @@ struct Attn2Params {
   int stagger;  // clocks by which query tile 1 starts behind tile 0 (softmax phases of the two warps of a scheduler interleave)
   unsigned int* trace;  // debug: phase timestamps of softmax warps 0 and 4 of CTA (0,0,0), [2][n_kv][8] (NULL: off)
 };
-static unsigned int* g_attn_trace = nullptr;
+unsigned int* g_attn_trace = nullptr;  // shared with fmha3_tc.cu
 
 constexpr int A2_BQ = 128;                    // rows per query tile (two tiles per CTA)
 constexpr int A2_BK = 128;                    // keys per block

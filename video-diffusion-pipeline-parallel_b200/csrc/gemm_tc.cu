@@ -194,7 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nstages = p.epi_dma ? Cfg::STAGES - Cfg::STEAL : Cfg::STAGES;  // smem ring depth of this launch
   __half* sBias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full) + 192);  // [BN] this tile's bias
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so that what the MMA issuer derives from it stays in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // work item = one tile (or, for CTA pairs, two vertically adjacent tiles sharing the N tile)
   const int cta_rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
@@ -366,13 +367,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {  // pairs: only the leader issues (for both CTAs)
+    // The WHOLE warp runs the loop and one elected lane executes the tcgen05 instructions.  Under `if (lane == 0)`
+    // the loop is divergent code: addresses and descriptors live in vector registers and every MMA pays a chain of
+    // R2UR moves - tools/ubench/mma.cu: 116 clocks per issued MMA that way (166 for N = 256), while the tensor pipe
+    // needs 80 for an N = 160 instruction and a lean converged loop issues at exactly the pipe's rate (64 / 80 / 128
+    // clocks for N = 128 / 160 / 256 = 8190 FLOP/clk/SM).  The mbarrier probe of the NEXT stage is issued before this
+    // stage's MMAs (a try_wait costs ~90 clocks even on a completed phase; its predicate is only consumed one
+    // k-block later).
+    if (cta_rank == 0) {  // pairs: only the leader CTA issues (for both CTAs)
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_f16(Cfg::MMA_N, false, TWO ? 256 : 128);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       int it = 0;  // tiles done by this CTA pair (ROT3 buffer rotation)
+      bool ready = false;  // full[stage] already seen complete (probed one k-block ahead)
       for (int item = 0; item < n_items; ++item, ++it) {
         const bool is_tail = item >= n_full_items;
         const int kb_begin = is_tail ? tail_kb0 : 0, kb_end = is_tail ? tail_kb1 : p.num_kb;
@@ -389,38 +400,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_after();
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full[stage], phase, 3);
+          if (!ready) mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == nstages) {
+            nstage = 0;
+            nphase ^= 1;
+          }
+          ready = mbar_test_wait(&full[nstage], nphase);  // non-blocking; a "not yet" only costs the blocking wait above
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
-            if constexpr (TWO) {
-              umma2_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-              if constexpr (Cfg::MMAS == 2)
-                umma2_f16(d_tmem2, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
-                          idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-            } else {
-              umma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
+              const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
+              if constexpr (TWO) {
+                umma2_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+                if constexpr (Cfg::MMAS == 2)
+                  umma2_f16(d_tmem2, da, make_smem_desc_sw128(b_addr + Cfg::B_BOX_ROWS * 128 + k * 32, 1024, 0),
+                            idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+              } else {
+                umma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+              }
             }
+            if constexpr (TWO)
+              umma2_commit(&empty[stage]);
+            else
+              umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
           }
-          if constexpr (TWO)
-            umma2_commit(&empty[stage]);
-          else
-            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          __syncwarp();
+          stage = nstage;
+          phase = nphase;
         }
-        if constexpr (Cfg::ROT3)
-          umma2_commit(&tfull[it & 1]);
-        else if constexpr (TWO)
-          umma2_commit(&tfull[as]);
-        else
-          umma_commit(&tfull[as]);  // accumulator complete
+        if (leader) {
+          if constexpr (Cfg::ROT3)
+            umma2_commit(&tfull[it & 1]);
+          else if constexpr (TWO)
+            umma2_commit(&tfull[as]);
+          else
+            umma_commit(&tfull[as]);  // accumulator complete
+        }
+        __syncwarp();
         if (++as == Cfg::NACC) {
           as = 0;
           aphase ^= 1;

@@ -1160,7 +1160,7 @@ int svdpp_unet_create(svdpp_unet** out, const svdpp_unet_config* cfg) {
   svdpp_unet* u = new svdpp_unet();
   u->cfg = *cfg;
   u->n_levels = cfg->n_levels;
-  if (u->cfg.attn_impl_long <= 0) u->cfg.attn_impl_long = 2;
+  if (u->cfg.attn_impl_long <= 0) u->cfg.attn_impl_long = 7;  // ping-pong FMHA (fmha3_tc.cu)
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       n <= 0) {

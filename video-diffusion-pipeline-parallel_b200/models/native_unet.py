@@ -149,7 +149,7 @@ class NativeUNet(nn.Module):
         self.attn_impl = attn_impl
         # spatial FMHA kernel for S >= 1024 (svdpp_attn_spatial_f16's impl): 4 = two query tiles per CTA with the
         # quarter-pipelined softmax (A/B in profiles/r2_*), 2 = the round-1 kernel
-        self.attn_impl_long = int(os.environ.get("SVDPP_ATTN_IMPL_LONG", "4")) if attn_impl_long is None else attn_impl_long
+        self.attn_impl_long = int(os.environ.get("SVDPP_ATTN_IMPL_LONG", "7")) if attn_impl_long is None else attn_impl_long
         self.orchestrator = (orchestrator or os.environ.get("SVDPP_ORCHESTRATOR", "c")).lower()
         if self.orchestrator not in ("c", "python"):
             raise ValueError("orchestrator must be 'c' or 'python'")
