@@ -52,5 +52,35 @@ def full(path):
         print()
 
 
+def traffic(path, out_json=None, note=""):
+    """DRAM bytes of the tcgen05 GEMM / conv launches of one forward (ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum,gpu__time_duration.sum -k regex:gemm_tc): the `roofline.traffic` source of bench.py."""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per_id = collections.defaultdict(dict)
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"].lower()
+        name = row["Metric Name"]
+        if name.startswith("dram__bytes"):
+            v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        elif name.startswith("gpu__time"):
+            v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)   # -> ms
+        per_id[row["ID"]][name] = v
+    rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in per_id.values())
+    wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in per_id.values())
+    ms = sum(d.get("gpu__time_duration.sum", 0.0) for d in per_id.values())
+    res = dict(launches=len(per_id), dram_read_bytes=rd, dram_write_bytes=wr,
+               traffic_bytes_per_launch=(rd + wr) / max(len(per_id), 1), ncu_time_ms=ms,
+               source="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:gemm_tc over one "
+                      "eager SVD-XT UNet forward (25 frames, 72x128 latent)" + (", " + note if note else ""))
+    print(json.dumps(res, indent=1))
+    if out_json:
+        json.dump(res, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
