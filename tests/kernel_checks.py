@@ -843,6 +843,15 @@ UNET_CHECKS = {
     "svd_steps_tc_cfg_pyorch": lambda: svd_steps(cfg_scale=3.0, orchestrator="python"),
     "svd_steps_tc_graph_pyorch": lambda: svd_steps(graph=True, orchestrator="python"),
 }
+# ragged shapes: frame counts and latent sizes whose token counts are no multiple of any tile (M tails at every level,
+# 1 frame = the temporal attention over a single key, 64 x 72 -> S = 4608 runs the ping-pong FMHA (impl 7) inside the UNet)
+UNET_CHECKS["unet_tiny_ragged_f5_24x40"] = lambda: unet_tiny(0, None, Fr=5, H=24, W=40)
+UNET_CHECKS["unet_tiny_ragged_f1_8x24"] = lambda: unet_tiny(0, None, Fr=1, H=8, W=24)
+UNET_CHECKS["unet_tiny_ragged_b2_f7_40x8"] = lambda: unet_tiny(0, None, B=2, Fr=7, H=40, W=8)
+UNET_CHECKS["unet_tiny_auto_impl_64x72"] = lambda: unet_tiny(3, None, Fr=2, H=64, W=72, cfg_over=dict(
+    block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4)))
+UNET_CHECKS["unet_tiny_tc_fmha7"] = lambda: unet_tiny(0, 7)
+UNET_CHECKS["svd_steps_ragged_cfg"] = lambda: svd_steps(cfg_scale=2.5, Fr=5, H=24, W=40)
 UNET_CHECKS["clip_vision_tiny"] = lambda: clip_vision()
 UNET_CHECKS["clip_vision_hd80"] = lambda: clip_vision(B=1, hidden_size=320, num_attention_heads=4, intermediate_size=1280,
                                                       num_hidden_layers=3, image_size=224, projection_dim=128)

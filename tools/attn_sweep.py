@@ -21,10 +21,11 @@ ap.add_argument("--staggers", default="0,300,600,900,1200")
 ap.add_argument("--iters", type=int, default=6)
 ap.add_argument("--key", default="fmha_stagger", help="tuning key the --staggers values are written to (fmha_stagger | fmha_handover)")
 ap.add_argument("--out", default="attn_sweep.json")
+ap.add_argument("--shapes", default="9216x5,2304x10", help="SxHEADS list (25 images each)")
 a = ap.parse_args()
 impls = [int(x) for x in a.impls.split(",")]
 staggers = [int(x) for x in a.staggers.split(",")]
-shapes = [(9216, 5, 25), (2304, 10, 25)]
+shapes = [(int(x.split("x")[0]), int(x.split("x")[1]), 25) for x in a.shapes.split(",")]
 res = []
 for S, heads, imgs in shapes:
     C = heads * 64
