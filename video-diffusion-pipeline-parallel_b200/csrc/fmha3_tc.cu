@@ -21,7 +21,9 @@
 // MUFU (wait for S, TMEM load, row maximum, wait for the previous PV product) while its partner exponentiates, then
 // runs its 128 exponentials alone at the full rate.  For that a single warp has to keep the pipe busy by itself:
 // the exponentials are issued in batches of 16, in place, and consumed (row sum, fp16 pack) one batch later, so no
-// instruction waits for a MUFU result that was issued just before it.  The hand-over is signalled a few batches
+// instruction waits for a MUFU result that was issued just before it (as far as ptxas lets it: at any optimisation level
+// it re-schedules the consumers to one pair behind their producers, volatile asm or not, so a lone warp reaches ~75 % of
+// the pipe's rate - tools/ubench/mix.cu - and the turns overlap by design).  The hand-over is signalled a few batches
 // before the end of the phase (the partner's wake-up latency overlaps the tail).
 // The MMA issuer warps run CONVERGED with one elected lane executing the tcgen05 instructions: under
 // `if (lane == 0) { loop }` the descriptors live in vector registers and every MMA pays a chain of R2UR moves
