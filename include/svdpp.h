@@ -128,7 +128,9 @@ typedef struct svdpp_attn_desc {
 /* impl: 0 = one 128-query tile per CTA, two CTAs per SM (short sequences); 2 = two query tiles per CTA, P in tensor memory
  * (round 1); 3 = 2 with two threads per row; 4 = 2 with the quarter-pipelined softmax (row maximum of the next 32 keys
  * computed under the exponentials of the current 32); 5 / 6 = 4 with every 8th / 4th group of four exponentials evaluated
- * as an FMA-pipe polynomial; 1 = plain CUDA-core kernel (bring-up cross-check).
+ * as an FMA-pipe polynomial; 7 = two query tiles per CTA whose exponential phases alternate through named barriers
+ * ("ping-pong", the default for S >= 1024 inside svdpp_unet_*; "fmha_handover" = batches of 16 exponentials before the end
+ * of a turn at which the partner warp is released); 1 = plain CUDA-core kernel (bring-up cross-check).
  * "fmha_stagger" (svdpp_set_tuning): SM clocks by which query tile 1 of impl 2..6 starts behind tile 0. */
 int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_stream stream);
 /* Debug: device buffer (>= 2 * ceil(S/128) * 8 uint32) that impl 2..6 fill with clock stamps of the softmax phases of two
