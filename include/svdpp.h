@@ -114,6 +114,32 @@ typedef struct svdpp_gemm_desc {
 int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused transformer feed-forward (C <= 320): y = epilogue( GEGLU(X W1^T + b1) W2^T + b2 ) in ONE kernel - the [M, 4C]
+ * gated intermediate stays in tensor memory (tcgen05.mma with the A operand in TMEM), never in HBM.
+ *   W1 [8C, C], b1 [8C]: the GEGLU projection with rows interleaved per 128 as [64 value | 64 gate] (value rows j, gate
+ *                        rows 4C + j of the diffusers weight, for j = 64 t .. 64 t + 63 in tile t)
+ *   W2 [w2_rows >= C, 4C] (row pitch ldw2), b2 [C]: ff.net.2 as stored by diffusers
+ *   y[m, n] = alpha * (acc + b2[n] + rowvec[rv(m), n]) + beta1 * R1[m, n] + beta2 * R2[m, n]      (as svdpp_gemm_f16)
+ * fp16 roundings as in the two-kernel path (projection, gelu(gate) and their product each rounded to fp16).
+ * Replaces: FeedForward(GEGLU) of BasicTransformerBlock / TemporalBasicTransformerBlock inside the UNet called at
+ * reference src/models/svd_unet.py:389-395 (two svdpp_gemm_f16 calls otherwise).
+ * -------------------------------------------------------------------------------------------*/
+typedef struct svdpp_ff_desc {
+  int32_t M, C;
+  const void* X;   int64_t ldx;           /* [M, C] */
+  const void* W1;  const void* b1;        /* [8C, C] interleaved, [8C] interleaved */
+  const void* W2;  int64_t ldw2; int32_t w2_rows;
+  const void* b2;
+  const void* rowvec; int64_t rv_ld;      /* [rows, C] or NULL; row = ((m / rv_hw) / rv_div) % rv_mod */
+  int32_t rv_hw, rv_div, rv_mod;
+  const void* R1;  int64_t ldr1; float beta1;
+  const void* R2;  int64_t ldr2; float beta2;
+  float alpha;
+  void* D;         int64_t ldd;           /* [M, C] */
+} svdpp_ff_desc;
+int svdpp_ff_geglu_f16(const svdpp_ff_desc* d, svdpp_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Spatial self-attention over S = H*W tokens per image, head_dim 64, no mask (tcgen05 FMHA).
  * q/k/v are column blocks of one [n_img*S, ld] matrix: head h of q at columns q_off + 64*h, etc.
  * Replaces: attn1 of BasicTransformerBlock (SDPA) inside the UNet.

@@ -170,6 +170,44 @@ def conv_temporal(B=2, Fr=5, H=4, W=32, C=64, impl=0):
     return _cmp(out, ref.reshape(-1, C))
 
 
+def ff_fused(M=1000, C=320, epilogue="res", seed=0):
+    """Fused GEGLU feed-forward against torch (fp32 maths on the fp16 weights) and against the two-kernel native path."""
+    from vdpp_b200.models.native_unet import interleave_geglu
+    inner = 4 * C
+    x = _rand(M, C, seed=seed + 1)
+    w1 = (_rand(2 * inner, C, seed=seed + 2).float() * C ** -0.5).half()
+    b1 = (_rand(2 * inner, seed=seed + 3).float() * 0.1).half()
+    w2 = (_rand(C, inner, seed=seed + 4).float() * inner ** -0.5).half()
+    b2 = (_rand(C, seed=seed + 5).float() * 0.1).half()
+    kw, ref_epi = {}, None
+    r1 = r2 = rv = None
+    if epilogue in ("res", "blend", "rowvec"):
+        r1 = _rand(M, C, seed=seed + 6)
+    if epilogue == "blend":
+        r2 = _rand(M, C, seed=seed + 7)
+        kw = dict(alpha=0.3, beta1=0.3, beta2=0.7)
+    if epilogue == "rowvec":
+        rv = _rand(5, C, seed=seed + 8)
+        kw = dict(rv_hw=7, rv_div=1, rv_mod=5)
+    w1i, b1i, _ = interleave_geglu(w1, b1, half=64)
+    guard = _Guarded(M, C)
+    native.ff_geglu(guard.out, x, w1i, b1i, w2, b2, r1=r1, r2=r2, rowvec=rv, **kw)
+    # reference with the fp16 roundings of the two-kernel path
+    proj = (x.float() @ w1.float().t() + b1.float()).half()
+    h = (proj[:, :inner] * F.gelu(proj[:, inner:].float()).half())
+    y = h.float() @ w2.float().t() + b2.float()
+    if rv is not None:
+        rows = (torch.arange(M, device=DEV) // 7) % 5
+        y = y + rv.float()[rows]
+    y = kw.get("alpha", 1.0) * y
+    if r1 is not None:
+        y = y + kw.get("beta1", 1.0) * r1.float()
+    if r2 is not None:
+        y = y + kw.get("beta2", 1.0) * r2.float()
+    torch.cuda.synchronize()
+    return _with_guard(_cmp(guard.out, y, rel=4e-3), guard)
+
+
 # ------------------------------------------------------------------------------------------ attention
 def attn_spatial(n_img=2, S=320, heads=2, impl=0, growing=False):
     C = heads * 64
@@ -637,6 +675,16 @@ ALL_CHECKS = {
                      ("144", dict(n_img=3, S=144, heads=2)), ("576", dict(n_img=2, S=576, heads=3)),
                      ("2304", dict(n_img=2, S=2304, heads=5)), ("rescale", dict(n_img=2, S=1000, heads=2, growing=True)),
                      ("rescale_late", dict(n_img=1, S=1200, heads=1, growing="late")))},
+    # fused GEGLU feed-forward (ff_fused.cu): the gated intermediate stays in tensor memory
+    "ff_fused_320_res": lambda: ff_fused(),
+    "ff_fused_320_plain": lambda: ff_fused(M=128 * 3, epilogue="none"),
+    "ff_fused_320_blend": lambda: ff_fused(M=40000, epilogue="blend"),      # ~2 tiles per CTA
+    "ff_fused_320_rowvec": lambda: ff_fused(M=777, epilogue="rowvec"),
+    "ff_fused_64": lambda: ff_fused(M=300, C=64),
+    "ff_fused_256_many": lambda: ff_fused(M=128 * 148 * 3 + 5, C=256),      # 3+ tiles per CTA, M tail
+    "ff_fused_320_odd_tiles": lambda: ff_fused(M=128 * 7 + 3, epilogue="blend"),   # odd tile count: one CTA of the last pair idles
+    **{f"ff_fused_{n}_nopair": _tuned_later("ff_fused", kw, ff_pair=0)
+       for n, kw in (("320_res", dict()), ("320_blend", dict(M=40000, epilogue="blend")), ("64", dict(M=300, C=64)))},
     # ping-pong kernel (impl 7, fmha3_tc.cu): the two tiles' exponential phases alternate through named barriers
     **{f"tc7_attn_spatial_{n}": (lambda kw=kw: attn_spatial(impl=7, **kw))
        for n, kw in (("64", dict(n_img=2, S=64, heads=1)), ("256", dict(n_img=1, S=256, heads=1)),

@@ -39,18 +39,19 @@ def test_struct_layout_matches_header():
     # svdpp_gemm_desc / svdpp_attn_desc are passed by pointer: sizes must agree with the C compiler
     import subprocess
     import tempfile
-    src = ('#include <stdio.h>\n#include "svdpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(svdpp_gemm_desc), '
+    src = ('#include <stdio.h>\n#include "svdpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(svdpp_gemm_desc), '
            'sizeof(svdpp_attn_desc), sizeof(svdpp_small_group), sizeof(svdpp_unet_config), sizeof(svdpp_tensor_desc), '
-           'sizeof(svdpp_handoff));return 0;}\n')
+           'sizeof(svdpp_handoff), sizeof(svdpp_ff_desc));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b, c_, u, t, h = map(int, subprocess.check_output([exe]).split())
+        a, b, c_, u, t, h, f = map(int, subprocess.check_output([exe]).split())
     assert a == ctypes.sizeof(native.GemmDesc) and b == ctypes.sizeof(native.AttnDesc)
     assert c_ == ctypes.sizeof(native.SmallGroup) == 32
     assert u == ctypes.sizeof(native.UNetConfig) and t == ctypes.sizeof(native.TensorDesc) and h == ctypes.sizeof(native.Handoff)
+    assert f == ctypes.sizeof(native.FfDesc)
 
 
 def test_unet_handle_host_side_errors():

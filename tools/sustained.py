@@ -78,6 +78,31 @@ def cases(frames):
     gemm_case("gemm_L0_K2880_pair320", M0, 320, 2880, 6)
     gemm_case("gemm_L1_K5760_pair320", M1, 640, 5760, 6)
 
+    def ff_case(name, M, Cc, fused):
+        def make():
+            inner = 4 * Cc
+            x = h(M, Cc, scale=0.5)
+            w1 = h(2 * inner, Cc, scale=Cc ** -0.5)
+            b1 = h(2 * inner, scale=0.1)
+            w2 = h(Cc, inner, scale=inner ** -0.5)
+            b2 = h(Cc, scale=0.1)
+            r1 = h(M, Cc)
+            o = torch.empty(M, Cc, device=DEV, dtype=torch.float16)
+            if fused:
+                w1i, b1i, _ = interleave_geglu(w1, b1, half=64)
+                return lambda: native.ff_geglu(o, x, w1i, b1i, w2, b2, r1=r1)
+            w1i, b1i, _ = interleave_geglu(w1, b1, half=128)
+            mid = torch.empty(M, inner, device=DEV, dtype=torch.float16)
+
+            def run():
+                native.gemm(mid, x, w1i, bias=b1i, geglu=True, n_store=inner, impl=3)
+                native.gemm(o, mid, w2, bias=b2, r1=r1, n_store=Cc, impl=6)
+            return run
+        out[name] = (make, 2.0 * M * Cc * 12 * Cc, "TFLOP")
+
+    ff_case("ff_L0_two_kernels", M0, 320, False)
+    ff_case("ff_L0_fused", M0, 320, True)
+
     def cublas_case(name, M, N, K):   # the library's kernel at the same shape: what does a joule buy there?
         def make():
             x = h(M, K, scale=0.5)

@@ -54,6 +54,9 @@ Tuning& tuning() {
     v.fmha_stagger = e != nullptr ? atoi(e) : 900;   // in-situ A/B (profiles/r2_ab_attn_insitu.json): 94.8 -> 92.9 ms per step with impl 4
     e = getenv("SVDPP_FMHA_HANDOVER");
     v.fmha_handover = e != nullptr ? atoi(e) : 2;
+    e = getenv("SVDPP_FF_PAIR");
+    v.ff_pair = e != nullptr ? atoi(e) : 1;
+    v.ff_dbg = 0;
     v.reverse = 0;
     v.reverse_gn_apply_same = 0;
     e = getenv("SVDPP_ZIGZAG");
@@ -133,6 +136,8 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
   if (strcmp(key, "fmha_handover") == 0) return &svdpp::tuning().fmha_handover;
+  if (strcmp(key, "ff_dbg") == 0) return &svdpp::tuning().ff_dbg;
+  if (strcmp(key, "ff_pair") == 0) return &svdpp::tuning().ff_pair;
   if (strcmp(key, "reverse") == 0) return &svdpp::tuning().reverse;
   if (strcmp(key, "reverse_gn_apply_same") == 0) return &svdpp::tuning().reverse_gn_apply_same;
   if (strcmp(key, "zigzag") == 0) return &svdpp::tuning().zigzag;

@@ -19,7 +19,7 @@ GEMM_BN = 160  # N tile of the tcgen05 GEMM; weights are padded / GEGLU-interlea
 
 EXPORTED_SYMBOLS = (
     "svdpp_abi_version", "svdpp_last_error", "svdpp_device_info", "svdpp_set_tuning", "svdpp_get_tuning",
-    "svdpp_gemm_f16",
+    "svdpp_gemm_f16", "svdpp_ff_geglu_f16",
     "svdpp_attn_spatial_f16", "svdpp_debug_attn_trace", "svdpp_attn_temporal_f16", "svdpp_groupnorm_workspace_bytes",
     "svdpp_groupnorm_silu", "svdpp_layernorm", "svdpp_linear_small", "svdpp_linear_small_grouped",
     "svdpp_sinusoid_embed",
@@ -57,6 +57,22 @@ class GemmDesc(C.Structure):
         ("conv_stride", C.c_int32), ("cHin", C.c_int32), ("cWin", C.c_int32),
         ("out_up", C.c_int32), ("out_up_y", C.c_int32), ("out_up_x", C.c_int32),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
+    ]
+
+
+class FfDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("C", C.c_int32),
+        ("X", C.c_void_p), ("ldx", C.c_int64),
+        ("W1", C.c_void_p), ("b1", C.c_void_p),
+        ("W2", C.c_void_p), ("ldw2", C.c_int64), ("w2_rows", C.c_int32),
+        ("b2", C.c_void_p),
+        ("rowvec", C.c_void_p), ("rv_ld", C.c_int64),
+        ("rv_hw", C.c_int32), ("rv_div", C.c_int32), ("rv_mod", C.c_int32),
+        ("R1", C.c_void_p), ("ldr1", C.c_int64), ("beta1", C.c_float),
+        ("R2", C.c_void_p), ("ldr2", C.c_int64), ("beta2", C.c_float),
+        ("alpha", C.c_float),
+        ("D", C.c_void_p), ("ldd", C.c_int64),
     ]
 
 
@@ -124,6 +140,7 @@ def _bind(lib):
     lib.svdpp_groupnorm_workspace_bytes.restype = C.c_size_t
     lib.svdpp_groupnorm_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.svdpp_gemm_f16.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_void_p]
+    lib.svdpp_ff_geglu_f16.argtypes = [C.POINTER(FfDesc), C.c_void_p]
     lib.svdpp_attn_spatial_f16.argtypes = [C.POINTER(AttnDesc), C.c_int, C.c_void_p]
     lib.svdpp_debug_attn_trace.argtypes = [C.c_void_p]
     lib.svdpp_attn_temporal_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -341,6 +358,32 @@ def gemm(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, *, bias=None, a2=N
         kind = "conv" if conv_dims is not None else ("geglu" if geglu else "linear")
         PROFILE.append((kind, 2.0 * d.M * N * K, (d.M, N, K), e0, e1))
     _count()
+    return out
+
+
+def ff_geglu(out: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, *,
+             rowvec=None, rv_hw: int = 1, rv_div: int = 1, rv_mod: int = 0, r1=None, beta1: float = 1.0, r2=None,
+             beta2: float = 1.0, alpha: float = 1.0) -> torch.Tensor:
+    """Fused feed-forward (svdpp_ff_geglu_f16): ``w1`` / ``b1`` interleaved per 128 rows as [64 value | 64 gate]
+    (``interleave_geglu(w, b, half=64)``), ``w2`` [>= C, 4C] as stored by diffusers (rows may be padded)."""
+    _req(out), _req(x), _req(w1), _req(w2)
+    d = FfDesc()
+    d.M, d.C = x.shape[0], x.shape[1]
+    d.X, d.ldx = x.data_ptr(), x.stride(0)
+    d.W1, d.b1 = w1.data_ptr(), b1.data_ptr()
+    d.W2, d.ldw2, d.w2_rows = w2.data_ptr(), w2.stride(0), w2.shape[0]
+    d.b2 = b2.data_ptr()
+    if rowvec is not None:
+        d.rowvec, d.rv_ld = rowvec.data_ptr(), rowvec.stride(0)
+    d.rv_hw, d.rv_div, d.rv_mod = rv_hw, rv_div, rv_mod
+    if r1 is not None:
+        d.R1, d.ldr1 = r1.data_ptr(), r1.stride(0)
+    if r2 is not None:
+        d.R2, d.ldr2 = r2.data_ptr(), r2.stride(0)
+    d.beta1, d.beta2, d.alpha = beta1, beta2, alpha
+    d.D, d.ldd = out.data_ptr(), out.stride(0)
+    _check(load().svdpp_ff_geglu_f16(C.byref(d), _stream()), "svdpp_ff_geglu_f16")
+    _count(1)
     return out
 
 
