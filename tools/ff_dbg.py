@@ -1,3 +1,7 @@
+"""Where does the fused feed-forward kernel (svdpp_ff_geglu_f16, csrc/ff_fused.cu) spend its time?  Level-0 shape
+(230400 x 320), boost clocks, with parts of the kernel switched off through the "ff_dbg" tuning bits (results are wrong
+then): 1 = no GELU arithmetic, 2 = no GEMM2, 4 = no final epilogue (residual loads, stores), 7 = all three.
+   python tools/ff_dbg.py [path/to/libsvdpp_variant.so]"""
 import sys, torch
 sys.path.insert(0,'/root/repo')
 import vdpp_b200
