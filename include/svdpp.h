@@ -156,7 +156,9 @@ typedef struct svdpp_attn_desc {
  * computed under the exponentials of the current 32); 5 / 6 = 4 with every 8th / 4th group of four exponentials evaluated
  * as an FMA-pipe polynomial; 7 = two query tiles per CTA whose exponential phases alternate through named barriers
  * ("ping-pong", the default for S >= 1024 inside svdpp_unet_*; "fmha_handover" = batches of 16 exponentials before the end
- * of a turn at which the partner warp is released); 1 = plain CUDA-core kernel (bring-up cross-check).
+ * of a turn at which the partner warp is released); 8 = 7 with two threads per row (16 softmax warps, the two half-row
+ * warps of a tile take their turn together; measured slower, kept selectable); 1 = plain CUDA-core kernel (bring-up
+ * cross-check).
  * "fmha_stagger" (svdpp_set_tuning): SM clocks by which query tile 1 of impl 2..6 starts behind tile 0. */
 int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_stream stream);
 /* Debug: device buffer (>= 2 * ceil(S/128) * 8 uint32) that impl 2..6 fill with clock stamps of the softmax phases of two

@@ -692,6 +692,16 @@ ALL_CHECKS = {
                      ("576", dict(n_img=2, S=576, heads=3)), ("2304", dict(n_img=2, S=2304, heads=5)),
                      ("rescale", dict(n_img=2, S=1000, heads=2, growing=True)),
                      ("rescale_late", dict(n_img=1, S=1200, heads=1, growing="late")))},
+    # two threads per row, the two tiles' half-row warps take turns in pairs (impl 8, fmha4_tc.cu)
+    **{f"tc8_attn_spatial_{n}": (lambda kw=kw: attn_spatial(impl=8, **kw))
+       for n, kw in (("64", dict(n_img=2, S=64, heads=1)), ("256", dict(n_img=1, S=256, heads=1)),
+                     ("tail", dict(n_img=2, S=320, heads=2)), ("144", dict(n_img=3, S=144, heads=2)),
+                     ("200", dict(n_img=2, S=200, heads=1)),
+                     ("576", dict(n_img=2, S=576, heads=3)), ("2304", dict(n_img=2, S=2304, heads=5)),
+                     ("rescale", dict(n_img=2, S=1000, heads=2, growing=True)),
+                     ("rescale_late", dict(n_img=1, S=1200, heads=1, growing="late")))},
+    **{f"tc8_attn_spatial_handover{h}": _tuned_later("attn_spatial", dict(impl=8, n_img=2, S=1000, heads=2, growing=True),
+                                                     fmha_handover_split=h) for h in (0, 3)},
     **{f"tc7_attn_spatial_handover{h}": _tuned_later("attn_spatial", dict(impl=7, n_img=2, S=1000, heads=2, growing=True), fmha_handover=h)
        for h in (0, 7)},
 }

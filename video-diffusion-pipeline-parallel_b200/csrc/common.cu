@@ -54,6 +54,8 @@ Tuning& tuning() {
     v.fmha_stagger = e != nullptr ? atoi(e) : 900;   // in-situ A/B (profiles/r2_ab_attn_insitu.json): 94.8 -> 92.9 ms per step with impl 4
     e = getenv("SVDPP_FMHA_HANDOVER");
     v.fmha_handover = e != nullptr ? atoi(e) : 2;
+    e = getenv("SVDPP_FMHA_HANDOVER_SPLIT");
+    v.fmha_handover_split = e != nullptr ? atoi(e) : 1;
     e = getenv("SVDPP_FF_PAIR");
     v.ff_pair = e != nullptr ? atoi(e) : 1;
     v.ff_dbg = 0;
@@ -136,6 +138,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
   if (strcmp(key, "fmha_handover") == 0) return &svdpp::tuning().fmha_handover;
+  if (strcmp(key, "fmha_handover_split") == 0) return &svdpp::tuning().fmha_handover_split;
   if (strcmp(key, "ff_dbg") == 0) return &svdpp::tuning().ff_dbg;
   if (strcmp(key, "ff_pair") == 0) return &svdpp::tuning().ff_pair;
   if (strcmp(key, "reverse") == 0) return &svdpp::tuning().reverse;

@@ -316,6 +316,7 @@ __global__ void attn_spatial_simt_kernel(const __half* qkv, long long ld, AttnPa
 namespace svdpp {
 int launch_attn_spatial2(const svdpp_attn_desc* d, int variant, cudaStream_t stream);  // fmha2_tc.cu
 int launch_attn_spatial3(const svdpp_attn_desc* d, cudaStream_t stream);               // fmha3_tc.cu
+int launch_attn_spatial4(const svdpp_attn_desc* d, cudaStream_t stream);               // fmha4_tc.cu
 }
 
 using namespace svdpp;
@@ -339,6 +340,7 @@ extern "C" int svdpp_attn_spatial_f16(const svdpp_attn_desc* d, int impl, svdpp_
   if (impl == 3) return launch_attn_spatial2(d, 2, stream);
   if (impl >= 4 && impl <= 6) return launch_attn_spatial2(d, impl, stream);
   if (impl == 7) return launch_attn_spatial3(d, stream);
+  if (impl == 8) return launch_attn_spatial4(d, stream);
   if (impl == 1) {
     const long long total = static_cast<long long>(d->n_img) * d->heads * d->S;
     attn_spatial_simt_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
