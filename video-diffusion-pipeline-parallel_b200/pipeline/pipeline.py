@@ -40,6 +40,27 @@ from .step_assignment import StepRange, assign_steps, assign_steps_uneven
 LOGGER = logging.getLogger(__name__)
 
 
+_NVTX = os.environ.get("SVDPP_NVTX", "0") not in ("", "0")
+
+
+class _nvtx:
+    """NVTX range around a stage's denoising steps when SVDPP_NVTX=1 (tracing; the reference only logs
+    wall-clock per step, pipeline.py:94-97).  A no-op otherwise and on CPU tensors / builds without CUDA."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self.on = _NVTX and torch.cuda.is_available()
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 @dataclass(frozen=True)
 class LatentSpec:
     """Shape/dtype/device every stage agrees on out of band (reference ``pipeline.py:25-34``)."""
@@ -175,7 +196,8 @@ class PipelineStage:
         verbose = self.logger.isEnabledFor(logging.INFO)
         for step in steps:
             t0 = time.time() if verbose else 0.0
-            latent = self.model(latent, step)
+            with _nvtx(f"stage{self.config.rank}/step{step}"):
+                latent = self.model(latent, step)
             if verbose:
                 self._log(f"step {step} completed in {(time.time() - t0) * 1000.0:.2f} ms")
         return latent
