@@ -683,6 +683,11 @@ ALL_CHECKS = {
     "ff_fused_64": lambda: ff_fused(M=300, C=64),
     "ff_fused_256_many": lambda: ff_fused(M=128 * 148 * 3 + 5, C=256),      # 3+ tiles per CTA, M tail
     "ff_fused_320_odd_tiles": lambda: ff_fused(M=128 * 7 + 3, epilogue="blend"),   # odd tile count: one CTA of the last pair idles
+    **{f"ff_fused_{n}_mc": _tuned_later("ff_fused", kw, ff_pair=1)       # TMA-multicast pairs with independent MMAs
+       for n, kw in (("320_res", dict()), ("320_blend", dict(M=40000, epilogue="blend")), ("320_odd_tiles", dict(M=128 * 7 + 3)))},
+    **{f"ff_fused_{n}_two": _tuned_later("ff_fused", kw, ff_pair=2)      # cta_group::2 pairs (the default): the leader issues M = 256 MMAs
+       for n, kw in (("320_res", dict()), ("320_blend", dict(M=40000, epilogue="blend")), ("64", dict(M=300, C=64)),
+                     ("320_odd_tiles", dict(M=128 * 7 + 3, epilogue="rowvec")), ("256_many", dict(M=128 * 148 * 3 + 5, C=256)))},
     **{f"ff_fused_{n}_nopair": _tuned_later("ff_fused", kw, ff_pair=0)
        for n, kw in (("320_res", dict()), ("320_blend", dict(M=40000, epilogue="blend")), ("64", dict(M=300, C=64)))},
     # ping-pong kernel (impl 7, fmha3_tc.cu): the two tiles' exponential phases alternate through named barriers

@@ -23,7 +23,7 @@ def t(n=10):
     for _ in range(n): native.ff_geglu(o,x,w1i,b1i,w2,b2,r1=r1)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n
-for pair in (1,):
+for pair in (1,2):
     native.set_tuning('ff_pair',pair)
     for dbg in (0,1,2,4,7):
         native.set_tuning('ff_dbg',dbg)

@@ -57,7 +57,7 @@ Tuning& tuning() {
     e = getenv("SVDPP_FMHA_HANDOVER_SPLIT");
     v.fmha_handover_split = e != nullptr ? atoi(e) : 1;
     e = getenv("SVDPP_FF_PAIR");
-    v.ff_pair = e != nullptr ? atoi(e) : 1;
+    v.ff_pair = e != nullptr ? atoi(e) : 2;
     v.ff_dbg = 0;
     v.reverse = 0;
     v.reverse_gn_apply_same = 0;

@@ -87,6 +87,14 @@ __device__ __forceinline__ void ff_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 
+__device__ __forceinline__ void ff_umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // TMA tensor load that lands at the same smem offset in every CTA of `mask` and signals the mbarrier at the same offset there
 __device__ __forceinline__ void ff_tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
   asm volatile(
@@ -105,10 +113,14 @@ __device__ __forceinline__ void ff_commit_mc(uint64_t* bar, uint16_t mask) {
 // k-block / W2 chunk and multicasts it into both CTAs' rings (the kernel re-reads all of W1 and W2 for every row tile -
 // 2.4 MB per tile, 4.3 GB per level-0 call, which is what the L2 -> SM path can deliver in ~0.36 ms; the pair halves it).
 // A ring slot is rewritten only when BOTH CTAs' MMAs have retired from it: every "empty" commit is multicast to the pair.
-template <bool PAIR>
+template <int MODE>
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW2, const FfParams p) {
+                const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmW2q, const FfParams p) {
+  constexpr bool PAIR = MODE == 1;   // two CTAs share the weight stream through TMA multicast, independent MMAs
+  constexpr bool TWO = MODE == 2;    // cta_group::2: the leader CTA issues M = 256 MMAs for both CTAs' row tiles
+  constexpr bool CLUSTER = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;                                         // [kb][128][64]
@@ -134,12 +146,22 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int lane = threadIdx.x & 31;
   // work item w = one row tile (PAIR: two adjacent row tiles, one per CTA of the cluster; both CTAs run the same number of
   // items - an odd tile count gives the last CTA an all-zero tile whose rows are never stored)
-  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int w_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int w_total = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int cta_rank = CLUSTER ? static_cast<int>(cluster_ctarank()) : 0;
+  const int w_first = CLUSTER ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int w_stride = CLUSTER ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int w_total = CLUSTER ? (p.m_tiles + 1) >> 1 : p.m_tiles;
   const int n_my_tiles = w_first < w_total ? (w_total - w_first + w_stride - 1) / w_stride : 0;
-  auto tile_of = [&](int it) { return PAIR ? 2 * (w_first + it * w_stride) + cta_rank : w_first + it * w_stride; };
+  auto tile_of = [&](int it) { return CLUSTER ? 2 * (w_first + it * w_stride) + cta_rank : w_first + it * w_stride; };
+  // TWO: every barrier the MMA issuer waits on lives in the LEADER CTA (rank 0); the follower's threads arrive remotely
+  auto arrive_leader = [&](uint64_t* bar) {
+    if constexpr (TWO)
+      mbar_arrive_cluster(bar, 0);
+    else
+      mbar_arrive(bar);
+  };
+  constexpr int W1_BYTES = TWO ? FF_W1_STAGE / 2 : FF_W1_STAGE;   // TWO: each CTA holds half of the B rows of an MMA
+  constexpr int W2_HALF_BYTES = TWO ? FF_W2_HALF / 2 : FF_W2_HALF;
+  constexpr int EPI_ARRIVALS = TWO ? 2 * FF_EPI_WARPS : FF_EPI_WARPS;
   constexpr uint16_t MC_MASK = 3;
 
   if (warp == 0 && lane == 0) {
@@ -147,29 +169,34 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW1h);
     tma_prefetch_desc(&tmW2);
-    mbar_init(x_full, 1);
+    mbar_init(x_full, TWO ? 2 : 1);  // TWO: both CTAs' producers arrive on the leader's barrier
     mbar_init(x_empty, 1);
     for (int s = 0; s < FF_W1_STAGES; ++s) {
-      mbar_init(&w1_full[s], 1);
+      mbar_init(&w1_full[s], TWO ? 2 : 1);
       mbar_init(&w1_empty[s], PAIR ? 2 : 1);  // pairs: both CTAs' MMAs must have retired from the slot
     }
     for (int s = 0; s < FF_W2_STAGES; ++s) {
-      mbar_init(&w2_full[s], 1);
+      mbar_init(&w2_full[s], TWO ? 2 : 1);
       mbar_init(&w2_empty[s], PAIR ? 2 : 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, FF_EPI_WARPS);
+    mbar_init(s_free, EPI_ARRIVALS);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&h_ready[s], FF_EPI_WARPS);
+      mbar_init(&h_ready[s], EPI_ARRIVALS);
       mbar_init(&h_free[s], 1);
     }
     mbar_init(y_full, 1);
-    mbar_init(y_free, FF_EPI_WARPS);
+    mbar_init(y_free, EPI_ARRIVALS);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc2(tmem_slot, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   pdl_launch_dependents();
   pdl_wait();
@@ -177,7 +204,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   for (int i = threadIdx.x; i < p.n_chunks * 128 / 8; i += FF_THREADS)
     reinterpret_cast<uint4*>(sB1)[i] = reinterpret_cast<const uint4*>(p.b1)[i];
   tc_fence_before();
-  if constexpr (PAIR)
+  if constexpr (CLUSTER)
     cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   else
     __syncthreads();
@@ -194,11 +221,29 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int it = 0; it < n_my_tiles; ++it) {
         const int m0 = tile_of(it) * FF_BM;
         mbar_wait(x_empty, (it & 1) ^ 1, 81);
-        mbar_expect_tx(x_full, p.kb * FF_XBLK);
-        for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(sX + kb * FF_XBLK, &tmX, x_full, kb * 64, m0);
+        if constexpr (TWO) {
+          if (cta_rank == 0)
+            mbar_expect_tx(x_full, 2 * p.kb * FF_XBLK);  // both CTAs' bytes land on the leader's barrier
+          else
+            mbar_arrive_cluster(x_full, 0);
+          for (int kb = 0; kb < p.kb; ++kb) tma2_load_2d(sX + kb * FF_XBLK, &tmX, x_full, kb * 64, m0);
+        } else {
+          mbar_expect_tx(x_full, p.kb * FF_XBLK);
+          for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(sX + kb * FF_XBLK, &tmX, x_full, kb * 64, m0);
+        }
         auto load_w2 = [&](int j) {
           const int s = g2 % FF_W2_STAGES;
           mbar_wait(&w2_empty[s], ((g2 / FF_W2_STAGES) & 1) ^ 1, 83);
+          if constexpr (TWO) {  // my 80 rows of each N = 160 half; the MMA reads the other 80 from the peer's smem
+            if (cta_rank == 0)
+              mbar_expect_tx(&w2_full[s], 2 * 2 * W2_HALF_BYTES);
+            else
+              mbar_arrive_cluster(&w2_full[s], 0);
+            tma2_load_2d(sW2 + s * FF_W2_STAGE, &tmW2q, &w2_full[s], j * 64, cta_rank * 80);
+            tma2_load_2d(sW2 + s * FF_W2_STAGE + W2_HALF_BYTES, &tmW2q, &w2_full[s], j * 64, 160 + cta_rank * 80);
+            ++g2;
+            return;
+          }
           mbar_expect_tx(&w2_full[s], FF_W2_STAGE);
           if constexpr (PAIR) {  // my 160-row half, into both CTAs
             ff_tma_load_2d_mc(sW2 + s * FF_W2_STAGE + cta_rank * FF_W2_HALF, &tmW2, &w2_full[s], j * 64, cta_rank * 160, MC_MASK);
@@ -212,6 +257,14 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int kb = 0; kb < p.kb; ++kb, ++g1) {
             const int s = g1 % FF_W1_STAGES;
             mbar_wait(&w1_empty[s], ((g1 / FF_W1_STAGES) & 1) ^ 1, 82);
+            if constexpr (TWO) {  // my 64 of the chunk's 128 rows
+              if (cta_rank == 0)
+                mbar_expect_tx(&w1_full[s], 2 * W1_BYTES);
+              else
+                mbar_arrive_cluster(&w1_full[s], 0);
+              tma2_load_2d(sW1 + s * FF_W1_STAGE, &tmW1h, &w1_full[s], kb * 64, j * 128 + cta_rank * 64);
+              continue;
+            }
             mbar_expect_tx(&w1_full[s], FF_W1_STAGE);
             if constexpr (PAIR)  // my half of the 128 rows, into both CTAs
               ff_tma_load_2d_mc(sW1 + s * FF_W1_STAGE + cta_rank * (FF_W1_STAGE / 2), &tmW1h, &w1_full[s], kb * 64,
@@ -237,14 +290,35 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
       if (it + 1 < n_my_tiles) {  // pace: one tile ahead of the epilogue is enough
-        mbar_wait(x_full, it & 1, 93);
+        if constexpr (TWO)
+          mbar_wait(y_full, it & 1, 93);  // (x_full only completes in the leader CTA)
+        else
+          mbar_wait(x_full, it & 1, 93);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+  } else if (warp == 1 && (!TWO || cta_rank == 0)) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane; TWO: leader CTA only)
     const bool leader = elect_one();
-    constexpr uint32_t idesc1 = make_idesc_f16(128, false);  // S: N = 128 (64 value + 64 gate rows of W1)
-    constexpr uint32_t idesc2 = make_idesc_f16(160, false);  // Y half: N = 160 rows of W2, K-major
+    constexpr uint32_t idesc1 = make_idesc_f16(128, false, TWO ? 256 : 128);  // S: N = 128 (64 value + 64 gate rows of W1)
+    constexpr uint32_t idesc2 = make_idesc_f16(160, false, TWO ? 256 : 128);  // Y half: N = 160 rows of W2, K-major
+    auto mma_ss = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+      if constexpr (TWO)
+        umma2_f16(d, da, db, idesc, acc);
+      else
+        umma_f16(d, da, db, idesc, acc);
+    };
+    auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
+      if constexpr (TWO)
+        ff_umma2_ts(d, a, db, idesc, acc);
+      else
+        ff_umma_ts(d, a, db, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {  // TWO: the completion is signalled at this offset in BOTH CTAs
+      if constexpr (TWO)
+        umma2_commit(bar);
+      else
+        umma_commit(bar);
+    };
     const uint32_t x_addr = smem_u32(sX);
     const uint64_t a_desc0 = make_smem_desc_sw128(x_addr, 1024, 0);
     const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(sW1), 1024, 0);
@@ -269,17 +343,17 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint64_t db = b_desc0 + static_cast<uint64_t>(s * (FF_W1_STAGE >> 4));
           if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_S, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) mma_ss(tmem_S, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
             if constexpr (PAIR)
               ff_commit_mc(&w1_empty[s], MC_MASK);
             else
-              umma_commit(&w1_empty[s]);
+              commit(&w1_empty[s]);
           }
           __syncwarp();
           ++g1;
         }
       }
-      if (leader) umma_commit(s_full);
+      if (leader) commit(s_full);
       __syncwarp();
       ++gs;
     };
@@ -296,14 +370,14 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (p.dbg & 2) break;
-          ff_umma_ts(tmem_Y, a_h + k * 8, db + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
-          ff_umma_ts(tmem_Y + 160, a_h + k * 8, db + (FF_W2_HALF >> 4) + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
+          mma_ts(tmem_Y, a_h + k * 8, db + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
+          mma_ts(tmem_Y + 160, a_h + k * 8, db + (W2_HALF_BYTES >> 4) + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&h_free[hb]);
+        commit(&h_free[hb]);
         if constexpr (PAIR)
           ff_commit_mc(&w2_empty[s], MC_MASK);
         else
-          umma_commit(&w2_empty[s]);
+          commit(&w2_empty[s]);
       }
       __syncwarp();
       ++g2;
@@ -319,12 +393,12 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (j + 1 < p.n_chunks) {
           gemm1(j + 1);
         } else {
-          if (leader) umma_commit(x_empty);  // every GEMM1 of this tile issued: x tile reusable once they retire
+          if (leader) commit(x_empty);  // every GEMM1 of this tile issued: x tile reusable once they retire
           __syncwarp();
         }
         gemm2(j, it);
       }
-      if (leader) umma_commit(y_full);
+      if (leader) commit(y_full);
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -346,7 +420,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);   // GEMM1 of the next chunk may overwrite S
+        if (lane == 0) arrive_leader(s_free);   // GEMM1 of the next chunk may overwrite S
         const __half* bv = sB1 + j * 128 + half * 32;
         const __half* bg = bv + 64;
         uint32_t hpk[16];
@@ -369,7 +443,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&h_ready[hb]);
+        if (lane == 0) arrive_leader(&h_ready[hb]);
       }
       // ---- final epilogue of the tile: this thread's row, columns [half*160, +160)
       mbar_wait(y_full, it & 1, 92);
@@ -399,7 +473,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (c == 4) {  // Y is in registers: the next tile's GEMM2 may start
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(y_free);
+          if (lane == 0) arrive_leader(y_free);
         }
         if (on) {
           float f[32];
@@ -455,13 +529,16 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 
   tc_fence_before();
-  if constexpr (PAIR)
+  if constexpr (CLUSTER)
     cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   else
     __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (TWO)
+      tmem_dealloc2(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -500,7 +577,7 @@ extern "C" int svdpp_ff_geglu_f16(const svdpp_ff_desc* d, svdpp_stream stream_) 
   p.D = static_cast<__half*>(d->D);
   p.ldd = d->ldd;
   p.dbg = tuning().ff_dbg;
-  CUtensorMap tmX, tmW1, tmW1h, tmW2;
+  CUtensorMap tmX, tmW1, tmW1h, tmW2, tmW2q;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->M)};
     uint64_t str[1] = {static_cast<uint64_t>(d->ldx) * 2};
@@ -520,22 +597,28 @@ extern "C" int svdpp_ff_geglu_f16(const svdpp_ff_desc* d, svdpp_stream stream_) 
     uint64_t str[1] = {static_cast<uint64_t>(d->ldw2) * 2};
     uint32_t box[2] = {64, 160};
     if (encode_tmap_f16(&tmW2, d->W2, 2, dims, str, box)) return -5;
+    uint32_t boxq[2] = {64, 80};
+    if (encode_tmap_f16(&tmW2q, d->W2, 2, dims, str, boxq)) return -5;
   }
   static bool configured = false;
   if (!configured) {
-    SVDPP_CUDA(cudaFuncSetAttribute(ff_geglu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
-    SVDPP_CUDA(cudaFuncSetAttribute(ff_geglu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    SVDPP_CUDA(cudaFuncSetAttribute(ff_geglu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    SVDPP_CUDA(cudaFuncSetAttribute(ff_geglu_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    SVDPP_CUDA(cudaFuncSetAttribute(ff_geglu_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     configured = true;
   }
-  const bool pair = tuning().ff_pair != 0 && p.m_tiles >= 2;
-  if (pair) {
+  const int mode = p.m_tiles >= 2 ? tuning().ff_pair : 0;   // 0 single CTAs, 1 multicast pairs, 2 cta_group::2 pairs
+  if (mode != 0) {
     const int pairs = (p.m_tiles + 1) / 2;
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-    SVDPP_CUDA(launch_kernel(ff_geglu_kernel<true>, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, 2, tmX, tmW1, tmW1h, tmW2, p));
+    if (mode == 2)
+      SVDPP_CUDA(launch_kernel(ff_geglu_kernel<2>, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, 2, tmX, tmW1, tmW1h, tmW2, tmW2q, p));
+    else
+      SVDPP_CUDA(launch_kernel(ff_geglu_kernel<1>, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, 2, tmX, tmW1, tmW1h, tmW2, tmW2q, p));
   } else {
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
-    SVDPP_CUDA(launch_kernel(ff_geglu_kernel<false>, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, 1, tmX, tmW1, tmW1h, tmW2, p));
+    SVDPP_CUDA(launch_kernel(ff_geglu_kernel<0>, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, 1, tmX, tmW1, tmW1h, tmW2, tmW2q, p));
   }
   return check_launch("ff_geglu_kernel");
 }
