@@ -923,6 +923,10 @@ UNET_CHECKS["vae_decode_tiny_b2"] = lambda: vae_decode(B=2, Fr=2, h=16, w=8)
 UNET_CHECKS["vae_decode_3level"] = lambda: vae_decode(B=1, Fr=2, h=8, w=16, block_out_channels=(64, 128, 256), layers_per_block=2)
 UNET_CHECKS["vae_encode_tiny"] = lambda: vae_encode()
 UNET_CHECKS["vae_encode_3level"] = lambda: vae_encode(N=1, H=128, W=128, block_out_channels=(64, 128, 256))
+# the transformer feed-forwards through the fused kernel (svdpp_ff_geglu_f16; "ff_fused", off by default)
+UNET_CHECKS["unet_tiny_tc_ff_fused"] = _tuned(UNET_CHECKS["unet_tiny_tc"], ff_fused=1)
+UNET_CHECKS["unet_tiny_ragged_ff_fused"] = _tuned(UNET_CHECKS["unet_tiny_ragged_b2_f7_40x8"], ff_fused=1)
+UNET_CHECKS["svd_steps_tc_cfg_ff_fused"] = _tuned(UNET_CHECKS["svd_steps_tc_cfg"], ff_fused=1)
 UNET_CHECKS["unet_tiny_tc_copyout"] = _tuned(UNET_CHECKS["unet_tiny_tc"], tma_store=0)
 UNET_CHECKS["unet_tiny_tc_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_tc"], zigzag=1)      # producer -> consumer direction flips
 UNET_CHECKS["unet_tiny_pair256_zigzag"] = _tuned(UNET_CHECKS["unet_tiny_pair256"], zigzag=1)

@@ -56,6 +56,8 @@ Tuning& tuning() {
     v.fmha_handover = e != nullptr ? atoi(e) : 2;
     e = getenv("SVDPP_FMHA_HANDOVER_SPLIT");
     v.fmha_handover_split = e != nullptr ? atoi(e) : 1;
+    e = getenv("SVDPP_FF_FUSED");
+    v.ff_fused = e != nullptr ? atoi(e) : 0;
     e = getenv("SVDPP_FF_PAIR");
     v.ff_pair = e != nullptr ? atoi(e) : 2;
     v.ff_dbg = 0;
@@ -139,6 +141,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
   if (strcmp(key, "fmha_handover") == 0) return &svdpp::tuning().fmha_handover;
   if (strcmp(key, "fmha_handover_split") == 0) return &svdpp::tuning().fmha_handover_split;
+  if (strcmp(key, "ff_fused") == 0) return &svdpp::tuning().ff_fused;
   if (strcmp(key, "ff_dbg") == 0) return &svdpp::tuning().ff_dbg;
   if (strcmp(key, "ff_pair") == 0) return &svdpp::tuning().ff_pair;
   if (strcmp(key, "reverse") == 0) return &svdpp::tuning().reverse;

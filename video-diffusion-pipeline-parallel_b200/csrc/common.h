@@ -55,6 +55,7 @@ struct Tuning {
   int fmha_stagger;         // two-tile FMHA: SM clocks by which query tile 1 starts behind tile 0 (0: together)
   int fmha_handover;        // ping-pong FMHA (impl 7): batches of 16 exponentials before the end of a turn at which the partner warp is released
   int fmha_handover_split;  // two-threads-per-row ping-pong FMHA (impl 8): the same, of the 4 batches of a turn
+  int ff_fused;             // svdpp_unet_*: feed-forwards of blocks with C <= 320 through the fused kernel (svdpp_ff_geglu_f16)
   int ff_dbg;               // fused feed-forward: timing experiments (results are wrong when non-zero)
   int ff_pair;              // fused feed-forward: 0 single CTAs, 1 clusters of two sharing the weight stream through TMA multicast, 2 cta_group::2 pairs (default)
   int reverse;              // GEMM / LayerNorm / GroupNorm launches walk their rows from the end (L2-friendly after a forward producer)

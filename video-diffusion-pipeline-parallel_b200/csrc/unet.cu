@@ -120,6 +120,7 @@ struct TrP {
   float eps = 1e-6f;
   Norm norm, norm1, norm3, t_norm_in, t_norm1, t_norm3;
   Lin proj_in, qkv1, out1, ff1, ff2, t_ffin1, t_ffin2, t_qkv, t_out1, t_ff1, t_ff2, proj_out;
+  Lin ff1f, t_ffin1f, t_ff1f;  // the GEGLU projections packed for the fused feed-forward kernel (C <= 320 only; else empty)
   int ca_off = 0, ca_c = 0, t_ca_off = 0, t_ca_c = 0;
   Small pos1, pos2;
   float alpha = 0.5f;
@@ -376,6 +377,22 @@ struct Loader {
     l.b = matrix(static_cast<const __half*>(b->data), 2 * inner, 1, 1, l.n_pad, 1, half, inner);
     return l;
   }
+  // the same projection interleaved per 128 rows as [64 value | 64 gate] for svdpp_ff_geglu_f16 (C <= 320)
+  Lin geglu_fused(const std::string& p) {
+    Lin l;
+    const svdpp_tensor_desc* w = get(p + ".weight", 2);
+    const svdpp_tensor_desc* b = get(p + ".bias");
+    if (!w || !b) return l;
+    const int inner = static_cast<int>(w->shape[0]) / 2, k = static_cast<int>(w->shape[1]);
+    if (k > 320 || k % 64 != 0 || inner != 4 * k) return l;
+    l.n = inner;
+    l.n_pad = 2 * inner;
+    l.k_pad = k;
+    l.geglu = true;
+    l.w = matrix(static_cast<const __half*>(w->data), 2 * inner, k, k, l.n_pad, k, 64, inner);
+    l.b = matrix(static_cast<const __half*>(b->data), 2 * inner, 1, 1, l.n_pad, 1, 64, inner);
+    return l;
+  }
   Lin fuse_qkv(const std::string& p) {
     Lin l;
     const svdpp_tensor_desc* q = get(p + ".to_q.weight", 2);
@@ -478,9 +495,11 @@ struct Loader {
     reg_cross(s + ".attn2", &P.ca_off, &P.ca_c);
     P.norm3 = norm(s + ".norm3");
     P.ff1 = geglu(s + ".ff.net.0.proj");
+    P.ff1f = geglu_fused(s + ".ff.net.0.proj");
     P.ff2 = lin(s + ".ff.net.2");
     P.t_norm_in = norm(t + ".norm_in");
     P.t_ffin1 = geglu(t + ".ff_in.net.0.proj");
+    P.t_ffin1f = geglu_fused(t + ".ff_in.net.0.proj");
     P.t_ffin2 = lin(t + ".ff_in.net.2");
     P.t_norm1 = norm(t + ".norm1");
     P.t_qkv = fuse_qkv(t + ".attn1");
@@ -488,6 +507,7 @@ struct Loader {
     reg_cross(t + ".attn2", &P.t_ca_off, &P.t_ca_c);
     P.t_norm3 = norm(t + ".norm3");
     P.t_ff1 = geglu(t + ".ff.net.0.proj");
+    P.t_ff1f = geglu_fused(t + ".ff.net.0.proj");
     P.t_ff2 = lin(t + ".ff.net.2");
     P.pos1 = small(p + ".time_pos_embed.linear_1");
     P.pos2 = small(p + ".time_pos_embed.linear_2");
@@ -694,6 +714,39 @@ struct Exec {
     tuning().reverse = 0;
     if (r != 0 && rc == 0) rc = r;
   }
+  // feed-forward: GEGLU projection l1 then l2 with epilogue e - as ONE kernel (svdpp_ff_geglu_f16) when the "ff_fused"
+  // switch is on and the block is narrow enough (l1f packed), else as two GEMMs through a [rows, 4C] intermediate
+  T feed_forward(const T& a, const Lin& l1, const Lin& l1f, const Lin& l2, const Epi& e) {
+    if (!live() || !(tuning().ff_fused && l1f.w != nullptr)) {  // (the dry run that sizes the arena always plans the larger path)
+      T f1 = linear(a, l1);
+      return linear(f1, l2, e);
+    }
+    T out = newbuf(a->rows, l2.n);
+    launches += 1;
+    out->hot = 0;
+    svdpp_ff_desc d{};
+    d.M = static_cast<int32_t>(a->rows);
+    d.C = l1f.k_pad;
+    d.X = a->ptr;
+    d.ldx = a->cols;
+    d.W1 = l1f.w;
+    d.b1 = l1f.b;
+    d.W2 = l2.w;
+    d.ldw2 = l2.k_pad;
+    d.w2_rows = l2.n_pad;
+    d.b2 = l2.b;
+    d.rowvec = e.rowvec;
+    d.rv_ld = e.rv_ld;
+    d.rv_hw = e.rv_hw; d.rv_div = e.rv_div; d.rv_mod = e.rv_mod;
+    if (e.r1) { d.R1 = e.r1->ptr; d.ldr1 = e.r1->cols; d.beta1 = e.beta1; }
+    if (e.r2) { d.R2 = e.r2->ptr; d.ldr2 = e.r2->cols; d.beta2 = e.beta2; }
+    d.alpha = e.alpha;
+    d.D = out->ptr;
+    d.ldd = out->cols;
+    const int r = svdpp_ff_geglu_f16(&d, stream);
+    if (r != 0 && rc == 0) rc = r;
+    return out;
+  }
   T linear(const T& a, const Lin& l, const Epi& e = Epi(), const T& a2 = nullptr) {
     T out = newbuf(a->rows, l.n);
     gemm_into(out, a->ptr, a->cols, a->rows, l, e, a2, a2 ? a->cols : 0, nullptr, nullptr, 0, -1, 1, 0, 0, nullptr, rev_for(a));
@@ -863,11 +916,9 @@ struct Exec {
     T hs;
     {
       T n3 = layernorm(h2, P.norm3);
-      T f1 = linear(n3, P.ff1);
-      n3.reset();
       Epi e;
       e.r1 = h2;
-      hs = linear(f1, P.ff2, e);
+      hs = feed_forward(n3, P.ff1, P.ff1f, P.ff2, e);
     }
     h2.reset();
     // --- temporal block on (hs + frame-position embedding); token (b,f,p) stays at row (b*F+f)*HW+p
@@ -875,12 +926,10 @@ struct Exec {
     T t1;
     {
       T nin = layernorm(hs, P.t_norm_in, pos, HW, F);
-      T f1 = linear(nin, P.t_ffin1);
-      nin.reset();
       Epi e;
       e.r1 = hs;
       e.rowvec = pos; e.rv_ld = C; e.rv_hw = HW; e.rv_div = 1; e.rv_mod = F;
-      t1 = linear(f1, P.t_ffin2, e);
+      t1 = feed_forward(nin, P.t_ffin1, P.t_ffin1f, P.t_ffin2, e);
     }
     T t2;
     {
@@ -903,14 +952,12 @@ struct Exec {
     T hb;
     {
       T n3t = layernorm(t2, P.t_norm3);
-      T f1 = linear(n3t, P.t_ff1);
-      n3t.reset();
       // blend fused into the last temporal GEMM: a*hs + (1-a)*(ff + t2)
       Epi e;
       e.alpha = 1.0f - a;
       e.r1 = t2; e.beta1 = 1.0f - a;
       e.r2 = hs; e.beta2 = a;
-      hb = linear(f1, P.t_ff2, e);
+      hb = feed_forward(n3t, P.t_ff1, P.t_ff1f, P.t_ff2, e);
     }
     t2.reset();
     hs.reset();
