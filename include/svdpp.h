@@ -279,6 +279,16 @@ int svdpp_flag_set(void* flag, uint32_t value, svdpp_stream stream);
  * >= n_valid (0: all n) are padding keys: ignored and written as 0.  The single-head, head_dim-512 attention of the VAE mid
  * blocks and the 257-token attention of the CLIP image encoder = GEMM (Q K^T) -> this -> GEMM (P V). */
 int svdpp_softmax_rows(void* x, int64_t ld, int32_t rows, int32_t n, int32_t n_valid, float scale, svdpp_stream stream);
+/* Whole attention of a short sequence in one launch: softmax(scale * Q K^T) V for every (image, head), S <= 512 keys held in
+ * shared memory, fp32 maths on fp16 inputs.  Replaces the CLIPAttention of the image encoder (transformers
+ * CLIPVisionModelWithProjection: 257 tokens, 16 heads of width 80; reference scripts/generate_video_demo.py:112-117), which as
+ * a per-head GEMM -> softmax -> transpose -> GEMM chain cost 2048 launches per image.  qkv is one matrix (row pitch ld) with
+ * head h of q / k / v at columns {q,k,v}_off + h * head_stride; every image owns S_pad rows of which the first S are tokens.
+ * out[row, h * out_head_stride + d]: d < head_dim the result, head_dim <= d < out_head_stride zeros; rows of padding tokens
+ * zeros.  head_dim % 8 == 0, <= 128; out_head_stride <= 128. */
+int svdpp_attn_small_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, int32_t head_stride,
+                         void* out, int64_t ldo, int32_t out_head_stride, int32_t n_img, int32_t S, int32_t S_pad,
+                         int32_t heads, int32_t head_dim, float scale, svdpp_stream stream);
 /* out[c, r] = in[r, c] for an fp16 matrix [R, C] (V -> V^T, the K-major B operand of the P V product). */
 int svdpp_transpose_f16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t R, int32_t C, svdpp_stream stream);
 /* TemporalDecoder.time_conv_out: Conv3d (3,1,1) over the frames of a 3-channel video, reading the channels-last output of

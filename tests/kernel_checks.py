@@ -501,6 +501,23 @@ def vae_encode(N=2, H=64, W=128, **over):
     return r
 
 
+def attn_small(n_img=2, S=257, S_pad=384, heads=3, hd=80, stride=128, ostride=128):
+    """svdpp_attn_small_f16 vs torch fp32 SDPA: padded head layout, padding tokens / padding columns written as zeros."""
+    width = 3 * heads * stride
+    qkv = _rand(n_img * S_pad, width, seed=5)
+    guard = _Guarded(n_img * S_pad, heads * ostride)
+    out = guard.out
+    out.fill_(float("nan"))              # every element of the output must be written
+    native.attn_small(out, qkv, n_img=n_img, S=S, S_pad=S_pad, heads=heads, head_dim=hd, q_off=0, k_off=heads * stride,
+                      v_off=2 * heads * stride, head_stride=stride, out_head_stride=ostride, scale=hd ** -0.5)
+    t = qkv.reshape(n_img, S_pad, 3, heads, stride)[:, :S, :, :, :hd].float()      # [n, S, 3, h, hd]
+    q, k, v = [t[:, :, i].transpose(1, 2) for i in range(3)]                        # [n, h, S, hd]
+    ref = torch.zeros(n_img, S_pad, heads, ostride, device=DEV)
+    ref[:, :S, :, :hd] = F.scaled_dot_product_attention(q, k, v).transpose(1, 2)
+    torch.cuda.synchronize()
+    return _with_guard(_cmp(out, ref.reshape(n_img * S_pad, heads * ostride), rel=2e-3), guard)
+
+
 def clip_vision(B=2, **over):
     """NativeCLIPVision vs the REAL transformers CLIPVisionModelWithProjection on the same weights (fp32 and fp16)."""
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
@@ -509,9 +526,12 @@ def clip_vision(B=2, **over):
                patch_size=14, projection_dim=64, hidden_act="gelu")
     cfg.update(over)
     torch.manual_seed(0)
+    attn, use_graph = cfg.pop("attn", "fused"), cfg.pop("use_graph", False)
     lib = CLIPVisionModelWithProjection(CLIPVisionConfig(**cfg)).to(DEV).half().eval()
-    nat = NativeCLIPVision(lib.state_dict(), config=cfg, device=DEV)
+    nat = NativeCLIPVision(lib.state_dict(), config=cfg, device=DEV, attn=attn, use_graph=use_graph)
     px = _rand(B, 3, cfg["image_size"], cfg["image_size"], seed=3)
+    if use_graph:      # capture on other pixels, then replay on the checked ones
+        nat(_rand(B, 3, cfg["image_size"], cfg["image_size"], seed=4))
     got = nat(px).image_embeds
     with torch.no_grad():
         ref16 = lib(pixel_values=px).image_embeds
@@ -568,6 +588,12 @@ ALL_CHECKS = {
     "layernorm_generic": lambda: layernorm(M=19, C=128, add=True),
     "softmax_rows": lambda: softmax_rows(),
     "softmax_rows_9216": lambda: softmax_rows(rows=33, n=9216, scale=512 ** -0.5),
+    # whole short-sequence attention in one launch (the CLIP image encoder's 257 tokens x 16 heads of width 80)
+    "attn_small_clip": lambda: attn_small(),
+    "attn_small_tiny": lambda: attn_small(n_img=1, S=17, S_pad=128, heads=4, hd=48, stride=128, ostride=128),
+    "attn_small_dense": lambda: attn_small(n_img=3, S=64, S_pad=64, heads=2, hd=64, stride=64, ostride=64),
+    "attn_small_hd128": lambda: attn_small(n_img=1, S=288, S_pad=288, heads=2, hd=128, stride=128, ostride=128),
+    "attn_small_long": lambda: attn_small(n_img=2, S=400, S_pad=512, heads=2, hd=40, stride=64, ostride=48),
     "transpose": lambda: transpose(),
     "transpose_9216x512": lambda: transpose(R=9216, C=512),
     "time_conv_out_fp32": lambda: time_conv_out(fp32=True),
@@ -709,6 +735,12 @@ ALL_CHECKS = {
                                                      fmha_handover_split=h) for h in (0, 3)},
     **{f"tc7_attn_spatial_handover{h}": _tuned_later("attn_spatial", dict(impl=7, n_img=2, S=1000, heads=2, growing=True), fmha_handover=h)
        for h in (0, 7)},
+    # a share of the exponentials on the FMA pipe (degree-3 polynomial, "fmha_poly" of every 16): every instantiation,
+    # plain / partial last block with masked keys / the lazy-rescale path
+    **{f"tc7_attn_spatial_poly{n}_{tag}": _tuned_later("attn_spatial", dict(impl=7, **kw), fmha_poly=n)
+       for n in (0, 2, 3, 4, 5, 6, 8)
+       for tag, kw in (("2304", dict(n_img=2, S=2304, heads=2)), ("tail", dict(n_img=2, S=1000, heads=2, growing=True)),
+                       ("144", dict(n_img=3, S=144, heads=2)))},
 }
 
 
@@ -918,6 +950,9 @@ UNET_CHECKS["svd_steps_ragged_cfg"] = lambda: svd_steps(cfg_scale=2.5, Fr=5, H=2
 UNET_CHECKS["clip_vision_tiny"] = lambda: clip_vision()
 UNET_CHECKS["clip_vision_hd80"] = lambda: clip_vision(B=1, hidden_size=320, num_attention_heads=4, intermediate_size=1280,
                                                       num_hidden_layers=3, image_size=224, projection_dim=128)
+UNET_CHECKS["clip_vision_hd80_gemm_attention"] = lambda: clip_vision(B=1, hidden_size=320, num_attention_heads=4, intermediate_size=1280,
+                                                                     num_hidden_layers=2, image_size=224, projection_dim=128, attn="gemm")
+UNET_CHECKS["clip_vision_tiny_graph"] = lambda: clip_vision(use_graph=True)
 UNET_CHECKS["vae_decode_tiny"] = lambda: vae_decode()
 UNET_CHECKS["vae_decode_tiny_b2"] = lambda: vae_decode(B=2, Fr=2, h=16, w=8)
 UNET_CHECKS["vae_decode_3level"] = lambda: vae_decode(B=1, Fr=2, h=8, w=16, block_out_channels=(64, 128, 256), layers_per_block=2)

@@ -1,7 +1,7 @@
 """Front / back end at full size (SVD: 576x1024 frames, latent 72x128): NativeVAE decode + encode and NativeCLIPVision
 (ViT-H/14) on the native kernels, against the torch restatement / the transformers class on torch's library kernels
 (the reference decodes in fp32: force_upcast).  Random-init weights of the real architectures.
-   python tools/vae_bench.py [--frames 25] [--chunk 14] [--no-library]   ->  gpurun_out/vae_bench.json"""
+   python tools/vae_bench.py [--frames 25] [--chunk 14] [--no-library] [--clip-only]   ->  gpurun_out/vae_bench.json"""
 import argparse
 import json
 import os
@@ -45,9 +45,19 @@ def main():
     ap.add_argument("--frames", type=int, default=25)
     ap.add_argument("--chunk", type=int, default=14)
     ap.add_argument("--no-library", action="store_true")
+    ap.add_argument("--clip-only", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     res = {"frames": a.frames, "chunk": a.chunk}
+    if not a.clip_only:
+        vae_part(a, dev, res)
+    clip_part(dev, res)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "vae_bench.json"), "w"), indent=1)
+    print(json.dumps(res))
+
+
+def vae_part(a, dev, res):
     torch.manual_seed(0)
     lib = AutoencoderKLTemporalDecoder().to(dev).half().eval()
     vae = NativeVAE(lib.state_dict(), device=dev)
@@ -77,6 +87,9 @@ def main():
         del lib32, frames_lib
     del lib, vae, frames
     torch.cuda.empty_cache()
+
+
+def clip_part(dev, res):
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
     cfg = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=16, image_size=224,
                patch_size=14, projection_dim=1024, hidden_act="gelu")
@@ -84,17 +97,26 @@ def main():
     clip_lib = CLIPVisionModelWithProjection(CLIPVisionConfig(**cfg)).to(dev).half().eval()
     clip = NativeCLIPVision(clip_lib.state_dict(), config=cfg, device=dev)
     px = torch.randn(1, 3, 224, 224, device=dev).half()
+    l0 = native.LAUNCHES
     ms, emb = timed(lambda: clip(px).image_embeds)
     res["clip_native_ms"] = ms
+    res["clip_launches"] = (native.LAUNCHES - l0) // 4
+    clip_g = NativeCLIPVision(clip_lib.state_dict(), config=cfg, device=dev, use_graph=True)
+    ms_g, emb_g = timed(lambda: clip_g(px).image_embeds)
+    res["clip_native_graph_ms"] = ms_g
+    res["clip_graph_equals_eager"] = bool(torch.equal(emb_g, emb))
+    del clip_g
+    clip_old = NativeCLIPVision(clip_lib.state_dict(), config=cfg, device=dev, attn="gemm")
+    ms_old, emb_old = timed(lambda: clip_old(px).image_embeds)
+    res["clip_native_gemm_attention_ms"] = ms_old
+    res["clip_fused_vs_gemm_attention"] = diff(emb, emb_old)
+    del clip_old
     with torch.no_grad():
         ms_lib, emb_lib = timed(lambda: clip_lib(pixel_values=px).image_embeds)
         emb32 = clip_lib.float()(pixel_values=px.float()).image_embeds
     res["clip_library_fp16_ms"] = ms_lib
     res["clip_native_vs_library_fp32"] = diff(emb, emb32)
     res["clip_library_fp16_vs_fp32"] = diff(emb_lib, emb32)
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "vae_bench.json"), "w"), indent=1)
-    print(json.dumps(res))
 
 
 if __name__ == "__main__":

@@ -54,6 +54,8 @@ Tuning& tuning() {
     v.fmha_stagger = e != nullptr ? atoi(e) : 900;   // in-situ A/B (profiles/r2_ab_attn_insitu.json): 94.8 -> 92.9 ms per step with impl 4
     e = getenv("SVDPP_FMHA_HANDOVER");
     v.fmha_handover = e != nullptr ? atoi(e) : 2;
+    e = getenv("SVDPP_FMHA_POLY");
+    v.fmha_poly = e != nullptr ? atoi(e) : 0;
     e = getenv("SVDPP_FMHA_HANDOVER_SPLIT");
     v.fmha_handover_split = e != nullptr ? atoi(e) : 1;
     e = getenv("SVDPP_FF_FUSED");
@@ -140,6 +142,7 @@ static int* tuning_slot(const char* key) {
   if (strcmp(key, "splitk_min_total_kb") == 0) return &svdpp::tuning().splitk_min_total_kb;
   if (strcmp(key, "fmha_stagger") == 0) return &svdpp::tuning().fmha_stagger;
   if (strcmp(key, "fmha_handover") == 0) return &svdpp::tuning().fmha_handover;
+  if (strcmp(key, "fmha_poly") == 0) return &svdpp::tuning().fmha_poly;
   if (strcmp(key, "fmha_handover_split") == 0) return &svdpp::tuning().fmha_handover_split;
   if (strcmp(key, "ff_fused") == 0) return &svdpp::tuning().ff_fused;
   if (strcmp(key, "ff_dbg") == 0) return &svdpp::tuning().ff_dbg;

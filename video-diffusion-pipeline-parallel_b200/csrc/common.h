@@ -54,6 +54,7 @@ struct Tuning {
   int splitk_min_total_kb;  // ... only for K / 64 >= this (the tail machinery costs ~20 us, a tile ~0.45 us per k-block)
   int fmha_stagger;         // two-tile FMHA: SM clocks by which query tile 1 starts behind tile 0 (0: together)
   int fmha_handover;        // ping-pong FMHA (impl 7): batches of 16 exponentials before the end of a turn at which the partner warp is released
+  int fmha_poly;            // ping-pong FMHA (impl 7): exponentials per batch of 16 evaluated by a degree-3 polynomial on the FMA pipe (0, 2..6, 8)
   int fmha_handover_split;  // two-threads-per-row ping-pong FMHA (impl 8): the same, of the 4 batches of a turn
   int ff_fused;             // svdpp_unet_*: feed-forwards of blocks with C <= 320 through the fused kernel (svdpp_ff_geglu_f16)
   int ff_dbg;               // fused feed-forward: timing experiments (results are wrong when non-zero)

@@ -96,6 +96,27 @@ __device__ __forceinline__ uint32_t a3_pack_half2(float a, float b) {
   asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));  // low half = a
   return r;
 }
+// exp2 on the FMA pipe for a share of the scores (tuning "fmha_poly"): Cody-Waite split x = n + f with the magic-number
+// add (n in the low mantissa bits), degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, a
+// sixth of the fp16 half-ulp P is rounded to anyway), n added into the exponent field.  8 FMA-pipe / ALU instructions
+// that issue in the 8-clock shadow of the neighbouring MUFU.EX2 instructions.
+__device__ __forceinline__ float a3_poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);                   // masked keys (-inf) and underflow: 2^-125, rounds to 0 in fp16
+  const float xf = x + 12582912.0f;        // 1.5 * 2^23: round-to-nearest integer part lands in the low mantissa bits
+  const float f = x - (xf - 12582912.0f);  // [-0.5, 0.5]
+  float pz = fmaf(0.0551716648042202f, f, 0.2426111251115799f);
+  pz = fmaf(pz, f, 0.6932609677314758f);
+  pz = fmaf(pz, f, 0.9999280571937561f);
+  return __uint_as_float(__float_as_uint(pz) + (__float_as_uint(xf) << 23));
+}
+// element e of a batch of 16 goes to the polynomial when NPOLY of 16 are asked for (spread evenly)
+template <int NPOLY>
+__device__ __forceinline__ constexpr bool a3_is_poly(int e) { return NPOLY > 0 && ((e * NPOLY) % 16) < NPOLY; }
+template <int NPOLY>
+__device__ __forceinline__ float a3_exp2_sel(float x, int e) {
+  return a3_is_poly<NPOLY>(e) ? a3_poly_exp2(x) : fast_exp2(x);
+}
+
 // named barriers of a warp pair (64 threads): sync = wait for the partner's arrive
 __device__ __forceinline__ void a3_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void a3_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -119,6 +140,7 @@ __device__ __forceinline__ float a3_max32(const uint32_t* x) {
   return fmaxf(fmaxf(a, b), fmaxf(c, d));
 }
 
+template <int NPOLY>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_spatial3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const Attn3Params p) {
@@ -335,10 +357,10 @@ attn_spatial3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             float x0, x1, x2, x3;
             a3_unpack_f2(xa, x0, x1);
             a3_unpack_f2(xb, x2, x3);
-            v[c] = __float_as_uint(fast_exp2(x0));
-            v[c + 1] = __float_as_uint(fast_exp2(x1));
-            v[c + 2] = __float_as_uint(fast_exp2(x2));
-            v[c + 3] = __float_as_uint(fast_exp2(x3));
+            v[c] = __float_as_uint(a3_exp2_sel<NPOLY>(x0, i));
+            v[c + 1] = __float_as_uint(a3_exp2_sel<NPOLY>(x1, i + 1));
+            v[c + 2] = __float_as_uint(a3_exp2_sel<NPOLY>(x2, i + 2));
+            v[c + 3] = __float_as_uint(a3_exp2_sel<NPOLY>(x3, i + 3));
           }
         }
         if (q == 8 - handover) {  // the partner may start: its wake-up overlaps my last batches
@@ -401,6 +423,17 @@ attn_spatial3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+template <int NPOLY>
+static int launch_attn3(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Attn3Params& p) {
+  static bool configured = false;
+  if (!configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(attn_spatial3_tc_kernel<NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
+    configured = true;
+  }
+  SVDPP_CUDA(launch_kernel(attn_spatial3_tc_kernel<NPOLY>, grid, dim3(A3_THREADS), A3_SMEM_BYTES, stream, 1, tmQ, tmKV, p));
+  return check_launch("attn_spatial3_tc_kernel");
+}
+
 int launch_attn_spatial3(const svdpp_attn_desc* d, cudaStream_t stream) {
   SVDPP_CHECK_ARG(d->heads <= 65535 && d->n_img <= 65535, "attn: grid too large");
   Attn3Params p{};
@@ -424,13 +457,18 @@ int launch_attn_spatial3(const svdpp_attn_desc* d, cudaStream_t stream) {
   if (encode_tmap_f16(&tmQ, d->qkv, 2, dims, str, box_q)) return -5;
   if (encode_tmap_f16(&tmKV, d->qkv, 2, dims, str, box_kv)) return -5;
   dim3 grid((d->S + 2 * A3_BQ - 1) / (2 * A3_BQ), d->heads, d->n_img);
-  static bool configured = false;
-  if (!configured) {
-    SVDPP_CUDA(cudaFuncSetAttribute(attn_spatial3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
-    configured = true;
+  switch (tuning().fmha_poly) {  // exponentials per batch of 16 evaluated on the FMA pipe
+    case 0: return launch_attn3<0>(grid, stream, tmQ, tmKV, p);
+    case 2: return launch_attn3<2>(grid, stream, tmQ, tmKV, p);
+    case 3: return launch_attn3<3>(grid, stream, tmQ, tmKV, p);
+    case 4: return launch_attn3<4>(grid, stream, tmQ, tmKV, p);
+    case 5: return launch_attn3<5>(grid, stream, tmQ, tmKV, p);
+    case 6: return launch_attn3<6>(grid, stream, tmQ, tmKV, p);
+    case 8: return launch_attn3<8>(grid, stream, tmQ, tmKV, p);
+    default: break;
   }
-  SVDPP_CUDA(launch_kernel(attn_spatial3_tc_kernel, grid, dim3(A3_THREADS), A3_SMEM_BYTES, stream, 1, tmQ, tmKV, p));
-  return check_launch("attn_spatial3_tc_kernel");
+  set_error("attn: fmha_poly must be one of 0, 2, 3, 4, 5, 6, 8 (exponentials of 16 on the FMA pipe)");
+  return -1;
 }
 
 }  // namespace svdpp

@@ -6,6 +6,10 @@
 //   transpose_kernel      V [S, C] -> V^T [C, S] so that P V is a GEMM with a K-major B operand
 //   time_conv_out_kernel  the decoder's last op, Conv3d (3,1,1) over frames on 3 channels, fused with the change from
 //                         channels-last [B*F, H*W, 3] to the caller's [B*F, 3, H, W]
+//   attn_small_kernel     whole attention of a short sequence (the CLIP image encoder: 257 tokens, 16 heads of width 80) in
+//                         one launch per layer: K and V of one (image, head) resident in shared memory, fp32 CUDA-core
+//                         maths (10 GFLOP over the 32 layers - launch count, not arithmetic, was the cost of the
+//                         GEMM -> softmax -> transpose -> GEMM chain per head: 2048 launches per image)
 #include <cuda_fp16.h>
 
 #include "common.h"
@@ -142,6 +146,151 @@ __global__ void time_conv_out_kernel(const __half* __restrict__ x, int xc, const
   }
 }
 
+// Attention over a short sequence.  Grid (ceil(S_pad / 32), heads, images), 256 threads: warp w owns queries 4w .. 4w + 3 of
+// the block's 32.  K / V of the (image, head) sit in shared memory as fp16 pairs with an ODD row pitch in words, so that
+// lanes reading consecutive keys (scores) or consecutive channel pairs (P V) never collide on a bank.
+//   scores   lane l holds keys l, l + 32, ... (KPL per lane) of its warp's four queries in registers, fp32
+//   softmax  warp shuffles; probabilities normalised in fp32 and parked in shared memory as one float4 (4 queries) per key
+//   P V      lane l owns channel pairs l and l + 32; one broadcast float4 + two V words per key
+// Rows [S, S_pad) of an image (padding tokens) and columns [head_dim, out_head_stride) of a head are written as zeros.
+template <int KPL>
+__global__ void __launch_bounds__(256)
+attn_small_kernel(const __half* __restrict__ qkv, long long ld, int q_off, int k_off, int v_off, int head_stride,
+                  __half* __restrict__ out, long long ldo, int out_head_stride, int S, int S_pad, int hd, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ uint32_t sm_small[];
+  const int hw = hd >> 1;                    // words (fp16 pairs) per head row
+  const int kw = hw | 1;                     // odd row pitch of K / V in shared memory
+  uint32_t* sK = sm_small;                   // [S][kw]
+  uint32_t* sV = sK + S * kw;                // [S][kw]
+  uint32_t* sQ = sm_small + ((2 * S * kw + 3) & ~3);   // [32][hw], 16-byte aligned
+  float4* sP = reinterpret_cast<float4*>(sQ + 32 * hw);  // [8 warps][KPL * 32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 32, head = blockIdx.y;
+  const long long row_base = static_cast<long long>(blockIdx.z) * S_pad;
+  const int ohw = out_head_stride >> 1;
+  __half* const out_head = out + head * out_head_stride;
+
+  if (q0 >= S) {  // padding tokens only: zeros
+    for (int idx = threadIdx.x; idx < 32 * ohw; idx += 256) {
+      const int r = idx / ohw, c = idx % ohw;
+      if (q0 + r < S_pad) *reinterpret_cast<uint32_t*>(out_head + (row_base + q0 + r) * ldo + 2 * c) = 0u;
+    }
+    return;
+  }
+  const int v8 = hd >> 3;  // 16-byte vectors per head row
+  for (int idx = threadIdx.x; idx < S * v8; idx += 256) {
+    const int r = idx / v8, c = idx % v8;
+    const __half* src = qkv + (row_base + r) * ld + head * head_stride + c * 8;
+    const uint4 k4 = *reinterpret_cast<const uint4*>(src + k_off);
+    const uint4 v4 = *reinterpret_cast<const uint4*>(src + v_off);
+    uint32_t* dk = sK + r * kw + c * 4;
+    uint32_t* dv = sV + r * kw + c * 4;
+    dk[0] = k4.x; dk[1] = k4.y; dk[2] = k4.z; dk[3] = k4.w;
+    dv[0] = v4.x; dv[1] = v4.y; dv[2] = v4.z; dv[3] = v4.w;
+  }
+  for (int idx = threadIdx.x; idx < 32 * v8; idx += 256) {
+    const int r = idx / v8, c = idx % v8;
+    uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
+    if (q0 + r < S) q4 = *reinterpret_cast<const uint4*>(qkv + (row_base + q0 + r) * ld + q_off + head * head_stride + c * 8);
+    *reinterpret_cast<uint4*>(sQ + r * hw + c * 4) = q4;
+  }
+  __syncthreads();
+
+  // ---- scores of queries 4w .. 4w + 3 against keys lane + 32 i
+  float acc[4][KPL];
+  int krow[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int k = lane + 32 * i;
+    krow[i] = (k < S ? k : S - 1) * kw;  // keys >= S are masked below; read a valid row meanwhile
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) acc[qi][i] = 0.f;
+  }
+  const uint32_t* qrow = sQ + (4 * warp) * hw;
+  for (int dp = 0; dp < hw; ++dp) {
+    float2 qf[4];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) qf[qi] = __half22float2(*reinterpret_cast<const __half2*>(qrow + qi * hw + dp));
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(sK + krow[i] + dp));
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) acc[qi][i] = fmaf(qf[qi].x, kf.x, fmaf(qf[qi].y, kf.y, acc[qi][i]));
+    }
+  }
+  // ---- softmax (fp32), probabilities to shared memory
+  float4* myP = sP + warp * (KPL * 32);
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) {
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i)
+      if (lane + 32 * i < S) mx = fmaxf(mx, acc[qi][i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      acc[qi][i] = lane + 32 * i < S ? fast_exp2((acc[qi][i] - mx) * scale_log2) : 0.f;
+      sum += acc[qi][i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) acc[qi][i] *= inv;
+  }
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) myP[lane + 32 * i] = make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]);
+  __syncwarp();
+  // ---- P V: lane owns channel pairs lane and lane + 32
+  const int dp0 = lane < hw ? lane : 0, dp1 = lane + 32 < hw ? lane + 32 : 0;
+  float2 o0[4], o1[4];
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) o0[qi] = o1[qi] = make_float2(0.f, 0.f);
+  for (int k = 0; k < S; ++k) {
+    const float4 pr = myP[k];
+    const float2 va = __half22float2(*reinterpret_cast<const __half2*>(sV + k * kw + dp0));
+    const float2 vb = __half22float2(*reinterpret_cast<const __half2*>(sV + k * kw + dp1));
+    const float pq[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      o0[qi].x = fmaf(pq[qi], va.x, o0[qi].x);
+      o0[qi].y = fmaf(pq[qi], va.y, o0[qi].y);
+      o1[qi].x = fmaf(pq[qi], vb.x, o1[qi].x);
+      o1[qi].y = fmaf(pq[qi], vb.y, o1[qi].y);
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) {
+    const int q = q0 + 4 * warp + qi;
+    if (q >= S_pad) continue;
+    __half* dst = out_head + (row_base + q) * ldo;
+    const bool real = q < S;
+    if (lane < ohw)
+      *reinterpret_cast<__half2*>(dst + 2 * lane) = (real && lane < hw) ? __floats2half2_rn(o0[qi].x, o0[qi].y) : __half2();
+    if (lane + 32 < ohw)
+      *reinterpret_cast<__half2*>(dst + 2 * (lane + 32)) =
+          (real && lane + 32 < hw) ? __floats2half2_rn(o1[qi].x, o1[qi].y) : __half2();
+  }
+}
+
+template <int KPL>
+static int launch_attn_small(dim3 grid, size_t smem, cudaStream_t stream, const __half* qkv, long long ld, int q_off, int k_off,
+                             int v_off, int head_stride, __half* out, long long ldo, int out_head_stride, int S, int S_pad, int hd,
+                             float scale_log2) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    SVDPP_CUDA(cudaFuncSetAttribute(attn_small_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  SVDPP_CUDA(launch_kernel(attn_small_kernel<KPL>, grid, dim3(256), smem, stream, 1, qkv, ld, q_off, k_off, v_off, head_stride, out,
+                           ldo, out_head_stride, S, S_pad, hd, scale_log2));
+  return check_launch("attn_small_kernel");
+}
+
 static inline unsigned vae_grid_for(long long n, int threads, int max_blocks = 148 * 16) {
   long long b = (n + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -162,6 +311,33 @@ extern "C" int svdpp_softmax_rows(void* x, int64_t ld, int32_t rows, int32_t n, 
   launch_kernel(softmax_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, static_cast<__half*>(x), static_cast<long long>(ld), n,
                 n_valid, scale * 1.4426950408889634f);
   return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int svdpp_attn_small_f16(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, int32_t head_stride,
+                                    void* out, int64_t ldo, int32_t out_head_stride, int32_t n_img, int32_t S, int32_t S_pad,
+                                    int32_t heads, int32_t head_dim, float scale, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(qkv && out && n_img > 0 && heads > 0 && S > 0 && S_pad >= S, "attn_small: bad arguments");
+  SVDPP_CHECK_ARG(S <= 512, "attn_small: S=%d exceeds 512 keys (longer sequences: svdpp_attn_spatial_f16)", S);
+  SVDPP_CHECK_ARG(head_dim >= 8 && head_dim <= 128 && head_dim % 8 == 0, "attn_small: head_dim=%d must be a multiple of 8, <= 128",
+                  head_dim);
+  SVDPP_CHECK_ARG(head_stride >= head_dim && out_head_stride >= head_dim && out_head_stride <= 128 && out_head_stride % 2 == 0,
+                  "attn_small: head strides must cover head_dim (output stride <= 128, even)");
+  SVDPP_CHECK_ARG(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && head_stride % 8 == 0 && ldo % 2 == 0,
+                  "attn_small: pitches and offsets must keep 16-byte alignment");
+  SVDPP_CHECK_ARG(heads <= 65535 && n_img <= 65535, "attn_small: grid too large");
+  const int hw = head_dim / 2, kw = hw | 1;
+  const int kpl = S <= 288 ? 9 : 16;
+  const size_t words = ((2 * static_cast<size_t>(S) * kw + 3) & ~static_cast<size_t>(3)) + 32 * hw + static_cast<size_t>(8) * kpl * 32 * 4;
+  const size_t smem = words * 4;
+  SVDPP_CHECK_ARG(smem <= 227 * 1024, "attn_small: S=%d x head_dim=%d needs %zu bytes of shared memory", S, head_dim, smem);
+  const dim3 grid((S_pad + 31) / 32, heads, n_img);
+  const float sl2 = scale * 1.4426950408889634f;
+  if (kpl == 9)
+    return launch_attn_small<9>(grid, smem, stream, static_cast<const __half*>(qkv), ld, q_off, k_off, v_off, head_stride,
+                                static_cast<__half*>(out), ldo, out_head_stride, S, S_pad, head_dim, sl2);
+  return launch_attn_small<16>(grid, smem, stream, static_cast<const __half*>(qkv), ld, q_off, k_off, v_off, head_stride,
+                               static_cast<__half*>(out), ldo, out_head_stride, S, S_pad, head_dim, sl2);
 }
 
 extern "C" int svdpp_transpose_f16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t R, int32_t C,

@@ -9,9 +9,12 @@ is pinned against the library itself, not against a restatement.
 
 How the shapes meet the kernels (head width 80 and 257 tokens are not tile multiples):
   * every image's 257 tokens live in 384 rows (3 x 128); the 127 padding rows stay finite and are never read back;
-  * q / k / v / out projections are packed with each head's 80 channels padded to 128 (zero rows / columns), so Q K^T
-    runs with K = 128 and the padding contributes exactly 0; attention per (image, head) is GEMM (Q K^T, 384 x 384) ->
-    row softmax with the 127 padding keys masked (``svdpp_softmax_rows(n_valid=257)``) -> GEMM (P V);
+  * q / k / v / out projections are packed with each head's 80 channels padded to 128 (zero rows / columns); attention
+    of all (image, head) pairs of a layer is ONE launch of ``svdpp_attn_small_f16`` (K / V of a head resident in shared
+    memory, fp32 maths; it writes zeros into the padding columns and padding-token rows).  ``attn="gemm"`` keeps the
+    first implementation - per head GEMM (Q K^T, 384 x 384, K = 128) -> row softmax with the 127 padding keys masked
+    (``svdpp_softmax_rows(n_valid=257)``) -> transpose -> GEMM (P V): 2048 launches per image, 27 ms against 10 ms for
+    the library, which is why the one-launch kernel exists;
   * the patch embedding (14 x 14 stride 14 convolution, no bias) is a GEMM over unfolded patches (K = 588 padded to 640)
     whose epilogue adds the position embedding row (``rowvec``) and writes straight into the token matrix;
   * ``fc1`` + exact GELU is the GEGLU epilogue with a constant value branch (zero weights, bias 1: 1 * gelu(gate)).
@@ -38,8 +41,13 @@ S_TILE = 128      # tokens per image padded to a multiple of this
 
 class NativeCLIPVision(nn.Module):
     def __init__(self, state_dict: Mapping[str, torch.Tensor], config: Optional[dict] = None,
-                 device: torch.device | str = "cuda"):
+                 device: torch.device | str = "cuda", attn: str = "fused", use_graph: bool = False):
         super().__init__()
+        self.use_graph = bool(use_graph)      # replay the launch sequence of a batch size as one CUDA graph
+        self._graphs = {}
+        if attn not in ("fused", "gemm"):
+            raise ValueError(f"attn must be 'fused' or 'gemm', got {attn!r}")
+        self.attn = attn
         cfg = dict(CLIP_VIT_H)
         if config is not None:
             src = config if isinstance(config, dict) else config.to_dict()
@@ -139,9 +147,29 @@ class NativeCLIPVision(nn.Module):
     @torch.no_grad()
     def forward(self, pixel_values: torch.Tensor, **_):
         """``pixel_values``: [B, 3, image_size, image_size] (the feature extractor's output).  Returns an object with
-        ``.image_embeds`` [B, projection_dim] (and ``.last_hidden_state`` [B, 257, hidden])."""
+        ``.image_embeds`` [B, projection_dim] (and ``.last_hidden_state`` [B, 257, hidden]).  With ``use_graph`` the
+        ~230 launches of a batch size are captured once (after one eager run) and replayed; the returned tensors are then
+        the graph's static outputs, overwritten by the next call."""
         if not pixel_values.is_cuda:
             raise NativeError("NativeCLIPVision needs CUDA tensors (there is no CPU path)")
+        if not self.use_graph:
+            return self._forward(pixel_values)
+        key = tuple(pixel_values.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = pixel_values.to(torch.float16).clone()
+            self._forward(static_in)                       # eager once: function attributes, tensor-map cache, allocator
+            torch.cuda.synchronize(self.device_)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._forward(static_in)
+            ent = self._graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(pixel_values)
+        g.replay()
+        return static_out
+
+    def _forward(self, pixel_values: torch.Tensor):
         cfg = self.cfg
         B, _, Hi, Wi = pixel_values.shape
         ps, C, H = cfg["patch_size"], cfg["hidden_size"], cfg["num_attention_heads"]
@@ -165,7 +193,10 @@ class NativeCLIPVision(nn.Module):
             n1 = native.layernorm(self._new(B * Sp, C), h, *L["ln1"], eps=cfg["layer_norm_eps"])
             qkv = self._linear(n1, L["qkv"])                                  # [B*Sp, 3 * heads * 128]
             o = self._new(B * Sp, H * HD_PAD)
-            for b in range(B):
+            if self.attn == "fused":
+                native.attn_small(o, qkv, n_img=B, S=S, S_pad=Sp, heads=H, head_dim=self.hd, q_off=0, k_off=H * HD_PAD,
+                                  v_off=2 * H * HD_PAD, head_stride=HD_PAD, out_head_stride=HD_PAD, scale=scale)
+            for b in range(B if self.attn == "gemm" else 0):
                 rows = slice(b * Sp, (b + 1) * Sp)
                 for hh in range(H):
                     q = qkv[rows, hh * HD_PAD:(hh + 1) * HD_PAD]

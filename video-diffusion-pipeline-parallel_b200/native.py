@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
     "svdpp_euler_vpred_step", "svdpp_euler_vpred_step_signal", "svdpp_flag_wait", "svdpp_flag_set", "svdpp_dummy_unet_step",
-    "svdpp_softmax_rows", "svdpp_transpose_f16", "svdpp_time_conv_out",
+    "svdpp_softmax_rows", "svdpp_transpose_f16", "svdpp_time_conv_out", "svdpp_attn_small_f16",
     "svdpp_unet_step_handoff", "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
     "svdpp_unet_forward", "svdpp_unet_forward_nhwc", "svdpp_unet_step", "svdpp_unet_last_launches", "svdpp_unet_destroy",
 )
@@ -188,6 +188,8 @@ def _bind(lib):
     lib.svdpp_flag_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]
     lib.svdpp_flag_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     lib.svdpp_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    lib.svdpp_attn_small_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     lib.svdpp_transpose_f16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.svdpp_time_conv_out.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int64, C.c_void_p]
@@ -570,6 +572,21 @@ def softmax_rows(x: torch.Tensor, scale: float = 1.0, n_valid: int = 0) -> torch
            "svdpp_softmax_rows")
     _count(1)
     return x
+
+
+def attn_small(out: torch.Tensor, qkv: torch.Tensor, *, n_img: int, S: int, S_pad: int, heads: int, head_dim: int, q_off: int,
+               k_off: int, v_off: int, head_stride: int, out_head_stride: int, scale: float) -> torch.Tensor:
+    """Attention of a short sequence (S <= 512) for every (image, head) in one launch; see ``svdpp_attn_small_f16``."""
+    _req(out), _req(qkv)
+    if qkv.shape[0] < n_img * S_pad or out.shape[0] < n_img * S_pad:
+        raise NativeError("attn_small: qkv / out have fewer than n_img * S_pad rows")
+    if max(q_off, k_off, v_off) + (heads - 1) * head_stride + head_dim > qkv.shape[1] or heads * out_head_stride > out.shape[1]:
+        raise NativeError("attn_small: head columns exceed the matrix width")
+    _check(load().svdpp_attn_small_f16(qkv.data_ptr(), qkv.stride(0), q_off, k_off, v_off, head_stride, out.data_ptr(),
+                                       out.stride(0), out_head_stride, n_img, S, S_pad, heads, head_dim, scale, _stream()),
+           "svdpp_attn_small_f16")
+    _count(1)
+    return out
 
 
 def transpose(out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
