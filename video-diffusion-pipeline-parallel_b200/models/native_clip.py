@@ -73,6 +73,23 @@ class NativeCLIPVision(nn.Module):
         self._build()
         self._sd = None
 
+    @classmethod
+    def from_pretrained(cls, model_id: str = "stabilityai/stable-video-diffusion-img2vid-xt",
+                        subfolder: str = "image_encoder", torch_dtype: torch.dtype = torch.float16,
+                        device: torch.device | str = "cuda", config: Optional[dict] = None, **kwargs) -> "NativeCLIPVision":
+        """``CLIPVisionModelWithProjection.from_pretrained(model_id, subfolder="image_encoder", torch_dtype=...)`` of
+        reference ``scripts/generate_video_demo.py:252-255``: a local snapshot directory (hub layout) or
+        ``random-init[:seed]``; there is no network (``frontend_weights.py``)."""
+        from . import frontend_weights as fw
+        if torch_dtype != torch.float16:
+            raise NativeError("NativeCLIPVision computes in fp16 with fp32 accumulation; torch_dtype must be torch.float16")
+        if fw.is_random_init(model_id):
+            sd = fw.random_state_dict(fw.clip_param_shapes(config), seed=fw.random_init_seed(model_id) + 2, device=device)
+        else:
+            sd, file_cfg = fw.load_component(model_id, subfolder, device=device)
+            config = {**(file_cfg or {}), **(config or {})}
+        return cls(sd, config=config, device=device, **kwargs)
+
     # ------------------------------------------------------------------ weight packing
     def _g(self, key: str) -> torch.Tensor:
         return self._sd[key].detach().to(self.device_, torch.float16)

@@ -165,6 +165,27 @@ class PipelineStage:
             self._peer = PeerHandoff(spec.shape, spec.dtype, spec.device)
         return self._peer
 
+    def negotiate_transport(self) -> Optional[str]:
+        """Collective: set up the peer-mapped slots now and, if the symmetric-memory rendezvous fails on ANY rank, put
+        every rank on NCCL send / recv instead.  Returns a note when it fell back, else None.  Optional - without it the
+        first handoff sets the slots up and raises on failure."""
+        if self.transport != "peer" or self.config.world_size <= 1:
+            return None
+        note = None
+        try:
+            self._peer_handoff()
+            ok = 1
+        except Exception as e:  # noqa: BLE001 - any failure means "not available here"
+            ok, note = 0, f"peer handoff unavailable on rank {self.config.rank}: {type(e).__name__}: {e}"
+        flag = torch.tensor([ok], device=self.config.latent_spec.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.transport, self._peer = "nccl", None
+            note = note or "peer handoff unavailable on another rank"
+            self.logger.warning("%s; using NCCL send/recv", note)
+            return note
+        return None
+
     def _run_steps_and_hand_over(self, latent: torch.Tensor, steps: Sequence[int]) -> None:
         """The slice ``steps`` on ``latent``, its LAST step writing straight into the next rank's receive slot and
         raising that rank's flag (models with ``supports_peer_out``); other models run normally and the result is
