@@ -23,6 +23,7 @@ What differs, all of it additive:
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import logging
 import os
@@ -249,6 +250,9 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
         stamp = int(time.time())
         if not args.no_files:
             out_dir.mkdir(parents=True, exist_ok=True)
+        # fingerprint of every final latent: equal across world sizes (the step pipeline is bit-identical to one GPU)
+        rec["latent_sha256"] = [hashlib.sha256(x.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
+                                for x in outs]
         t0 = _sync_time(device)
         for latents in outs:
             frames_all.append(decode_latents(latents, vae, args.num_frames, decode_chunk_size=args.decode_chunk_size))
