@@ -15,6 +15,9 @@ What differs, all of it additive:
 * the ranks run ``PipelineStage.run_many`` (stream-ordered, peer-mapped handoff on GPUs) instead of blocking
   ``dist.send`` / ``dist.recv`` per sample; ``--allow-uneven`` lifts the reference's ``total_steps % world == 0`` rule
   (25 steps on 2 / 4 / 8 GPUs), ``--transport nccl`` keeps NCCL send / recv;
+* ``--schedule ring`` places stage s of sample v on rank ``(v + s) % world`` (``PipelineStage.run_many_ring``): the same
+  slices and the same per-sample arithmetic (final latents SHA-256-equal), no fill / drain bubble, and every rank decodes
+  and writes the samples that finish on it, each printing its own ``GENERATE_JSON=`` line;
 * the noise augmentation of the conditioning image draws from a generator seeded with ``--seed`` so that every rank
   holds the same conditioning by construction (the reference relies on equal default seeds);
 * outputs: ``.gif`` through PIL (and ``.mp4`` when ``imageio`` is importable - it is not in this image), ``--save-frames``
@@ -60,6 +63,9 @@ def build_parser() -> argparse.ArgumentParser:
     # extensions
     p.add_argument("--decode-chunk-size", type=int, default=4, help="frames per VAE decode call (reference main: 4)")
     p.add_argument("--allow-uneven", action="store_true", help="first total_steps %% world stages take one step more")
+    p.add_argument("--schedule", default="fixed", choices=["fixed", "ring"],
+                   help="fixed: stage s on rank s (the reference); ring: stage s of sample v on rank (v + s) %% world - no "
+                        "fill / drain bubble, equal stage lengths, every rank decodes and writes the samples that end on it")
     p.add_argument("--transport", default=None, choices=["nccl", "peer"], help="stage handoff (default: peer on GPUs)")
     p.add_argument("--save-frames", action="store_true", help="also write every frame as PNG")
     p.add_argument("--no-files", action="store_true", help="generate and time only, write nothing")
@@ -170,6 +176,7 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
     dtype = torch.float16
+    ring = distributed and args.schedule == "ring"
     last = rank == world - 1
     if distributed:
         from ..distributed.backend import resolve_backend
@@ -203,7 +210,7 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
         num_frames=args.num_frames, noise_aug_strength=args.noise_aug_strength, generator=gen)
     rec["encode_s"] = _sync_time(device) - t0
     del image_encoder
-    if distributed and not last:
+    if distributed and not last and not ring:
         vae = None
     guidance = args.guidance_scale if args.guidance_scale and args.guidance_scale > 1.0 else None
     model.set_conditioning(image_embeddings=image_embeddings, image_latents=image_latents, fps=args.fps,
@@ -234,23 +241,28 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
     LOGGER.info("Rank %d: steps %d to %d; generating %d samples (guidance_scale=%s)", rank, stage.step_range.start,
                 stage.step_range.end - 1, args.num_samples, guidance)
     t0 = _sync_time(device)
-    outs = stage.run_many(args.num_samples, input_supplier=supplier if rank == 0 else None) or []
-    if rank == 0:
+    if ring:
+        done = stage.run_many_ring(args.num_samples, input_supplier=supplier)
+    else:
+        done = list(enumerate(stage.run_many(args.num_samples, input_supplier=supplier if rank == 0 else None) or []))
+    sample_ids, outs = [i for i, _ in done], [x for _, x in done]
+    if rank == 0 and not ring:
         mark()
     rec["diffusion_s"] = _sync_time(device) - t0
-    if rank == 0:      # this rank's stage time per sample (the whole denoising loop when world_size == 1); sample 0 warms up
+    if rank == 0 and not ring:      # this rank's stage time per sample (the whole denoising loop when world_size == 1); sample 0 warms up
         rec["stage_s_by_sample"] = [round(a.elapsed_time(b) / 1000.0, 4) for a, b in zip(marks[:-1], marks[1:])]
     rec["diffusion_s_per_sample"] = rec["diffusion_s"] / args.num_samples
 
     frames_all: List[torch.Tensor] = []
     files: List[str] = []
-    if last:
+    if last or (ring and outs):
         out_dir = Path(args.output_dir)
         stem_in = "synthetic" if args.input_image.startswith("synthetic") else Path(args.input_image).stem
         stamp = int(time.time())
         if not args.no_files:
             out_dir.mkdir(parents=True, exist_ok=True)
         # fingerprint of every final latent: equal across world sizes (the step pipeline is bit-identical to one GPU)
+        rec["samples"] = sample_ids
         rec["latent_sha256"] = [hashlib.sha256(x.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
                                 for x in outs]
         t0 = _sync_time(device)
@@ -260,7 +272,7 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
         rec["decode_s_per_sample"] = rec["decode_s"] / max(len(outs), 1)
         rec["frames_finite"] = bool(all(torch.isfinite(f).all().item() for f in frames_all))
         t0 = time.perf_counter()
-        for idx, frames in enumerate(frames_all):
+        for idx, frames in zip(sample_ids, frames_all):
             if args.no_files:
                 break
             stem = str(out_dir / f"{stem_in}_{stamp}_s{idx}_seed{args.seed + idx}")
