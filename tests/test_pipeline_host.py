@@ -180,6 +180,43 @@ def _single_process(total_steps, n_samples=3):
     return out
 
 
+def _negotiate_worker(rank, world, port, total_steps, n_samples, q):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    torch.set_num_threads(1)
+    init_distributed(backend="gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    ts = list(reversed(range(total_steps)))
+    stage = PipelineStage(_model(), PipelineConfig(total_steps, world, rank, ts, _spec()), transport="peer")
+    note = stage.negotiate_transport()        # CPU tensors: the peer-mapped slots cannot exist -> every rank drops to send / recv
+    assert note is not None and stage.transport == "nccl" and stage._peer is None
+    assert stage.negotiate_transport() is None            # nothing left to negotiate
+    with torch.no_grad():
+        outs = stage.run_many(n_samples, input_supplier=_supplier if rank == 0 else None)
+    if rank == world - 1:
+        q.put([_sha(o) for o in outs])
+    dist.barrier()
+    finalize_distributed()
+
+
+@pytest.mark.timeout(300)
+def test_transport_negotiation_falls_back_on_every_rank():
+    """``transport="peer"`` where the peer-mapped handoff cannot be set up (CPU / gloo here; a box without symmetric memory
+    in production): ``negotiate_transport`` is collective, all ranks agree on send / recv, and the results are unchanged."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_negotiate_worker, args=(r, 2, port, 28, 2, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == _single_process(28, 2)
+    # one process: nothing to negotiate, whatever the transport
+    solo = PipelineStage(_model(), PipelineConfig(4, 1, 0, [3, 2, 1, 0], _spec()), transport="peer")
+    assert solo.negotiate_transport() is None and solo.transport == "peer"
+
+
 @pytest.mark.timeout(300)
 def test_world_size_invariance_even_split():
     want = _single_process(28)
