@@ -297,6 +297,16 @@ int svdpp_transpose_f16(const void* in, int64_t ld_in, void* out, int64_t ld_out
 int svdpp_time_conv_out(const void* x, int32_t x_channels, const void* w, const void* bias, void* out, int32_t out_fp32,
                         int32_t B, int32_t F, int64_t HW, svdpp_stream stream);
 
+/* Output format of the image -> video run (reference scripts/generate_video_demo.py:198-222: frames -> uint8 -> file).
+ * frames: one video [3, F, H, W] in [-1, 1], fp32 (is_fp32) or fp16, element (c, f, y, x) at c * stride_c + f * stride_f +
+ * y * W + x (the permuted view decode_latents returns: stride_c = H * W, stride_f = 3 * H * W).  rgb (or null): packed bytes
+ * [F, H, W, 3] = ((v + 1) / 2 * 255).clamp(0, 255) truncated, bit-identical to the reference's torch expression.  idx (or
+ * null): [F, H, W] indices r * 42 + g * 6 + b into the fixed 6 x 7 x 6 colour cube (levels k * 255 / 5, k * 255 / 6,
+ * k * 255 / 5), with a 4 x 4 ordered dither when dither != 0 - a GIF frame that needs no palette search on the host.
+ * W % 4 == 0, strides % 4 == 0. */
+int svdpp_frames_to_bytes(const void* frames, int32_t is_fp32, int64_t stride_c, int64_t stride_f, int32_t F, int32_t H,
+                          int32_t W, void* rgb, void* idx, int32_t dither, svdpp_stream stream);
+
 /* DummyUNet step (reference src/models/dummy_unet.py:37-59), fp32, [B, C, F, H, W]:
  *   out = x + tanh_scale * conv3d(silu(conv3d(x, w1, b1)), w2, b2) + layernorm_C(x) */
 int svdpp_dummy_unet_step(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

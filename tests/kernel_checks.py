@@ -451,6 +451,47 @@ def time_conv_out(B=2, Fr=5, H=6, W=10, fp32=True):
     return _cmp(out, ref, rel=2e-3, floor=2e-3)
 
 
+BAYER4 = [[0, 8, 2, 10], [12, 4, 14, 6], [3, 11, 1, 9], [15, 7, 13, 5]]
+
+
+def cube_index_reference(rgb_u8, dither=True):
+    """numpy restatement of the fixed-palette quantiser of svdpp_frames_to_bytes (test oracle): rgb uint8 [F, H, W, 3] ->
+    index uint8 [F, H, W] = r * 42 + g * 6 + b with level = min(L - 1, floor(v * (L - 1) / 255 + threshold)) in fp32."""
+    import numpy as np
+    Fr, H, W, _ = rgb_u8.shape
+    thr = ((np.array(BAYER4, dtype=np.float32) + np.float32(0.5)) / np.float32(16)) if dither else np.full((4, 4), 0.5, np.float32)
+    t = thr[np.arange(H)[:, None] & 3, np.arange(W)[None, :] & 3][None]                       # [1, H, W]
+    lv = []
+    for c, L in enumerate((6, 7, 6)):
+        v = rgb_u8[..., c].astype(np.float32) * (np.float32(L - 1) / np.float32(255)) + t
+        lv.append(np.minimum(v.astype(np.int32), L - 1))
+    return (lv[0] * 42 + lv[1] * 6 + lv[2]).astype(np.uint8)
+
+
+def frames_to_bytes(Fr=5, H=18, W=32, dtype=torch.float32, dither=True, permuted=True):
+    """RGB bytes bit-equal to the reference script's torch expression (generate_video_demo.py:198-209), palette indices
+    bit-equal to the numpy restatement; input as the permuted view decode_latents returns, values beyond [-1, 1]."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    base = (torch.rand(Fr, 3, H, W, device=DEV, generator=g) * 2.6 - 1.3).to(dtype)       # [F, 3, H, W] as the decoder writes it
+    base[0, :, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, -0.999, 0.999, 1.0 - 2.0 / 255, -2.0, 2.0], device=DEV, dtype=dtype)
+    frames = base.permute(1, 0, 2, 3) if permuted else base.permute(1, 0, 2, 3).contiguous()   # [3, F, H, W]
+    pad = 64
+    rgb_buf = torch.full((Fr * H * W * 3 + 2 * pad,), 77, dtype=torch.uint8, device=DEV)
+    rgb, idx = native.frames_to_bytes(frames, rgb=True, palette=True, dither=dither)
+    only_idx = native.frames_to_bytes(frames, rgb=False, palette=True, dither=dither)[1]
+    only_rgb = native.frames_to_bytes(frames, rgb=True, palette=False)[0]
+    want = ((frames.float().permute(1, 2, 3, 0) + 1) / 2 * 255).clamp(0, 255).to(torch.uint8)      # the reference's expression
+    torch.cuda.synchronize()
+    ok_rgb = torch.equal(rgb, want) and torch.equal(only_rgb, want)
+    want_idx = torch.from_numpy(cube_index_reference(want.cpu().numpy(), dither)).to(DEV)
+    ok_idx = torch.equal(idx, want_idx) and torch.equal(only_idx, want_idx) and int(idx.max()) < 252
+    # the palette entry of every index is within one cube step of the byte it stands for
+    pal = torch.tensor(native.cube_palette(), device=DEV, dtype=torch.int32).reshape(256, 3)
+    err = (pal[idx.long()] - want.int()).abs().amax().item()
+    del rgb_buf
+    return dict(max_err=float(err), tol=52.0, ok=bool(ok_rgb and ok_idx and err <= 52), rgb_equal=bool(ok_rgb), idx_equal=bool(ok_idx))
+
+
 def _tiny_vae(seed=0, **over):
     from oracle.vae_torch import AutoencoderKLTemporalDecoder, tiny_vae_config
     from vdpp_b200.models.native_vae import NativeVAE
@@ -596,6 +637,9 @@ ALL_CHECKS = {
     "attn_small_long": lambda: attn_small(n_img=2, S=400, S_pad=512, heads=2, hd=40, stride=64, ostride=48),
     "transpose": lambda: transpose(),
     "transpose_9216x512": lambda: transpose(R=9216, C=512),
+    "frames_to_bytes_fp32": lambda: frames_to_bytes(),
+    "frames_to_bytes_fp16_contiguous": lambda: frames_to_bytes(Fr=1, H=7, W=12, dtype=torch.float16, permuted=False),
+    "frames_to_bytes_nodither_large": lambda: frames_to_bytes(Fr=3, H=576, W=1024, dither=False),
     "time_conv_out_fp32": lambda: time_conv_out(fp32=True),
     "time_conv_out_fp16": lambda: time_conv_out(B=1, Fr=1, fp32=False),
     "handoff_flags_cfg": lambda: handoff_flags(True),

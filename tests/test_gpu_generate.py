@@ -56,9 +56,18 @@ def test_generate_video_equals_its_composition(tmp_path, capsys, guidance):
     assert len(line) == 1
     printed = json.loads(line[0][len("GENERATE_JSON="):])
     assert printed["diffusion_s"] > 0 and printed["decode_s"] > 0 and len(printed["files"]) == 2
-    for path in printed["files"]:
+    import numpy as np
+    for k, path in enumerate(printed["files"]):
         with Image.open(path) as g:
             assert g.n_frames == 3 and g.size == (128, 128)
+            # quantised on the GPU into the fixed colour cube: every pixel within one cube step of the RGB bytes
+            g.seek(1)
+            back = np.asarray(g.convert("RGB"), dtype=np.int32)
+        rgb = gv.frames_to_uint8(frames[k])
+        assert rgb.shape == (3, 128, 128, 3) and rgb.dtype == np.uint8
+        assert np.abs(back - rgb[1].astype(np.int32)).max() <= 52
+        want = ((frames[k][0].permute(1, 2, 3, 0) + 1) / 2 * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
+        assert np.array_equal(rgb, want)              # the reference's expression, bit for bit
     assert len([f for f in os.listdir(tmp_path) if f.endswith(".png")]) == 6
 
     # the same run put together by hand from the public pieces

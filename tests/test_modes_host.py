@@ -121,8 +121,8 @@ def test_tools_and_entry_points_compile():
     import glob
     import py_compile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"),
-                                                               os.path.join(root, "__graft_entry__.py")]
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "scripts", "*.py")) + [
+        os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
     assert len(files) >= 15
     for f in files:
         py_compile.compile(f, doraise=True)

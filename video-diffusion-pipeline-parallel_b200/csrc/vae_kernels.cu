@@ -6,6 +6,10 @@
 //   transpose_kernel      V [S, C] -> V^T [C, S] so that P V is a GEMM with a K-major B operand
 //   time_conv_out_kernel  the decoder's last op, Conv3d (3,1,1) over frames on 3 channels, fused with the change from
 //                         channels-last [B*F, H*W, 3] to the caller's [B*F, 3, H, W]
+//   frames_to_bytes_kernel the output format of the run: decoded frames [3, F, H, W] in [-1, 1] -> packed RGB bytes [F, H, W, 3]
+//                         (the reference's ((x + 1) / 2 * 255).clamp(0, 255).to(uint8), bit for bit) and / or indices into a
+//                         fixed 6 x 7 x 6 colour cube with 4 x 4 ordered dither, so that the GIF writer on the host only
+//                         has to LZW-pack (its own adaptive palette search costs 5 s per 25-frame 576 x 1024 video)
 //   attn_small_kernel     whole attention of a short sequence (the CLIP image encoder: 257 tokens, 16 heads of width 80) in
 //                         one launch per layer: K and V of one (image, head) resident in shared memory, fp32 CUDA-core
 //                         maths (10 GFLOP over the 32 layers - launch count, not arithmetic, was the cost of the
@@ -291,6 +295,75 @@ static int launch_attn_small(dim3 grid, size_t smem, cudaStream_t stream, const 
   return check_launch("attn_small_kernel");
 }
 
+// ------------------------------------------------------------------------------------ frames -> bytes
+__device__ __forceinline__ float4 load_quad(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_quad(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// ((x + 1) / 2 * 255).clamp(0, 255).to(uint8): every operation rounded on its own, as torch's elementwise kernels
+__device__ __forceinline__ unsigned to_byte(float x) {
+  float v = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 255.0f);
+  v = fminf(fmaxf(v, 0.0f), 255.0f);          // NaN -> 0
+  return static_cast<unsigned>(v);            // truncation
+}
+// level of byte v in a cube axis of L levels: floor(v * (L - 1) / 255 + threshold), threshold in (0, 1)
+__device__ __forceinline__ unsigned cube_level(unsigned v, int L, float thr) {
+  const float t = __fadd_rn(__fmul_rn(static_cast<float>(v), static_cast<float>(L - 1) / 255.0f), thr);
+  const int q = static_cast<int>(t);
+  return static_cast<unsigned>(q > L - 1 ? L - 1 : q);
+}
+__constant__ float kBayer4[16] = {0.5f / 16,  8.5f / 16,  2.5f / 16,  10.5f / 16, 12.5f / 16, 4.5f / 16, 14.5f / 16, 6.5f / 16,
+                                  3.5f / 16,  11.5f / 16, 1.5f / 16,  9.5f / 16,  15.5f / 16, 7.5f / 16, 13.5f / 16, 5.5f / 16};
+
+// x: element (c, f, p) at x[c * sc + f * sf + p], p = y * W + col, W % 4 == 0.  One thread per 4 pixels of a row: three
+// 16-byte (fp32) / 8-byte (fp16) loads, 12 bytes of RGB and 4 bytes of indices out, all aligned.  HBM-bound.
+template <typename T>
+__global__ void __launch_bounds__(256) frames_to_bytes_kernel(const T* __restrict__ x, long long sc, long long sf, int F,
+                                                              long long HW, int W, unsigned char* __restrict__ rgb,
+                                                              unsigned char* __restrict__ idx, int dither) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long qpf = HW >> 2, quads = qpf * F;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < quads;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = q / qpf, p = (q - f * qpf) << 2;
+    const T* src = x + f * sf + p;
+    const float4 c0 = load_quad(src), c1 = load_quad(src + sc), c2 = load_quad(src + 2 * sc);
+    const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
+    unsigned R[4], G[4], B[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      R[j] = to_byte(r[j]);
+      G[j] = to_byte(g[j]);
+      B[j] = to_byte(b[j]);
+    }
+    const long long o = f * HW + p;
+    if (rgb != nullptr) {
+      uint3 w;
+      w.x = R[0] | (G[0] << 8) | (B[0] << 16) | (R[1] << 24);
+      w.y = G[1] | (B[1] << 8) | (R[2] << 16) | (G[2] << 24);
+      w.z = B[2] | (R[3] << 8) | (G[3] << 16) | (B[3] << 24);
+      unsigned* dst = reinterpret_cast<unsigned*>(rgb + o * 3);
+      dst[0] = w.x;
+      dst[1] = w.y;
+      dst[2] = w.z;
+    }
+    if (idx != nullptr) {
+      const int y = static_cast<int>(p / W);        // the quad starts at a column that is a multiple of 4
+      unsigned packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float thr = dither ? kBayer4[(y & 3) * 4 + j] : 0.5f;
+        packed |= (cube_level(R[j], 6, thr) * 42u + cube_level(G[j], 7, thr) * 6u + cube_level(B[j], 6, thr)) << (8 * j);
+      }
+      *reinterpret_cast<unsigned*>(idx + o) = packed;
+    }
+  }
+}
+
 static inline unsigned vae_grid_for(long long n, int threads, int max_blocks = 148 * 16) {
   long long b = (n + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -363,4 +436,23 @@ extern "C" int svdpp_time_conv_out(const void* x, int32_t x_channels, const void
                   x_channels, static_cast<const __half*>(w), static_cast<const __half*>(bias), static_cast<__half*>(out), B, F,
                   static_cast<long long>(HW));
   return check_launch("time_conv_out_kernel");
+}
+
+extern "C" int svdpp_frames_to_bytes(const void* frames, int32_t is_fp32, int64_t stride_c, int64_t stride_f, int32_t F,
+                                     int32_t H, int32_t W, void* rgb, void* idx, int32_t dither, svdpp_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SVDPP_CHECK_ARG(frames != nullptr && (rgb != nullptr || idx != nullptr), "frames_to_bytes: null pointer");
+  SVDPP_CHECK_ARG(F > 0 && H > 0 && W > 0 && W % 4 == 0, "frames_to_bytes: W=%d must be a positive multiple of 4", W);
+  SVDPP_CHECK_ARG(stride_c % 4 == 0 && stride_f % 4 == 0, "frames_to_bytes: strides must be multiples of 4 elements");
+  const long long HW = static_cast<long long>(H) * W;
+  const unsigned grid = vae_grid_for(HW / 4 * F, 256);
+  if (is_fp32)
+    launch_kernel(frames_to_bytes_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(frames),
+                  static_cast<long long>(stride_c), static_cast<long long>(stride_f), F, HW, W, static_cast<unsigned char*>(rgb),
+                  static_cast<unsigned char*>(idx), dither);
+  else
+    launch_kernel(frames_to_bytes_kernel<__half>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const __half*>(frames),
+                  static_cast<long long>(stride_c), static_cast<long long>(stride_f), F, HW, W, static_cast<unsigned char*>(rgb),
+                  static_cast<unsigned char*>(idx), dither);
+  return check_launch("frames_to_bytes_kernel");
 }

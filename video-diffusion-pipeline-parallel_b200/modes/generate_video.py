@@ -126,15 +126,34 @@ def load_feature_extractor(model_id: str):
 
 # ---------------------------------------------------------------------------------------------- frames out
 def frames_to_uint8(frames: torch.Tensor):
-    """``[B, 3, F, H, W]`` in [-1, 1] -> ``[F, H, W, 3]`` uint8 of the first batch element (reference :198-209)."""
+    """``[B, 3, F, H, W]`` in [-1, 1] -> ``[F, H, W, 3]`` uint8 of the first batch element (reference :198-209).  Frames on
+    a GPU go through ``svdpp_frames_to_bytes`` (one pass, bit-identical); CPU tensors through the reference's expression."""
+    if frames.is_cuda and frames.shape[-1] % 4 == 0:
+        from .. import native
+        return native.frames_to_bytes(frames[0], rgb=True, palette=False)[0].cpu().numpy()
     f = frames[0].permute(1, 2, 3, 0)
     return ((f + 1) / 2 * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
 
 
 def save_gif(frames: torch.Tensor, output_path: str, fps: int) -> None:
+    """GIF of the first batch element.  Frames on a GPU are quantised there (fixed 6 x 7 x 6 colour cube, ordered dither:
+    ``svdpp_frames_to_bytes``) and the host only LZW-packs them - PIL's own per-frame palette search, which CPU tensors
+    still get, takes about 5 s per 25-frame 576 x 1024 video."""
     from PIL import Image
-    imgs = [Image.fromarray(a) for a in frames_to_uint8(frames)]
-    imgs[0].save(output_path, save_all=True, append_images=imgs[1:], duration=max(int(round(1000 / fps)), 1), loop=0)
+    duration = max(int(round(1000 / fps)), 1)
+    if frames.is_cuda and frames.shape[-1] % 4 == 0:
+        from .. import native
+        idx = native.frames_to_bytes(frames[0], rgb=False, palette=True)[1].cpu().numpy()
+        pal = native.cube_palette()
+        imgs = []
+        for a in idx:
+            im = Image.fromarray(a, "P")
+            im.putpalette(pal)
+            imgs.append(im)
+        imgs[0].save(output_path, save_all=True, append_images=imgs[1:], duration=duration, loop=0, optimize=False)
+    else:
+        imgs = [Image.fromarray(a) for a in frames_to_uint8(frames)]
+        imgs[0].save(output_path, save_all=True, append_images=imgs[1:], duration=duration, loop=0)
     LOGGER.info("GIF saved to: %s", output_path)
 
 

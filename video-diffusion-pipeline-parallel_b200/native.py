@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "svdpp_sinusoid_embed",
     "svdpp_upsample2x_nhwc", "svdpp_im2col_nhwc", "svdpp_pack_unet_input", "svdpp_nhwc_to_bfchw",
     "svdpp_euler_vpred_step", "svdpp_euler_vpred_step_signal", "svdpp_flag_wait", "svdpp_flag_set", "svdpp_dummy_unet_step",
-    "svdpp_softmax_rows", "svdpp_transpose_f16", "svdpp_time_conv_out", "svdpp_attn_small_f16",
+    "svdpp_softmax_rows", "svdpp_transpose_f16", "svdpp_time_conv_out", "svdpp_attn_small_f16", "svdpp_frames_to_bytes",
     "svdpp_unet_step_handoff", "svdpp_unet_create", "svdpp_unet_load_weights", "svdpp_unet_weight_bytes", "svdpp_unet_workspace_bytes",
     "svdpp_unet_forward", "svdpp_unet_forward_nhwc", "svdpp_unet_step", "svdpp_unet_last_launches", "svdpp_unet_destroy",
 )
@@ -191,6 +191,8 @@ def _bind(lib):
     lib.svdpp_attn_small_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     lib.svdpp_transpose_f16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.svdpp_frames_to_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.svdpp_time_conv_out.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int64, C.c_void_p]
     lib.svdpp_unet_last_launches.restype = C.c_longlong
@@ -596,6 +598,36 @@ def transpose(out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
                                       _stream()), "svdpp_transpose_f16")
     _count(1)
     return out
+
+
+CUBE_LEVELS = (6, 7, 6)       # the fixed colour cube of svdpp_frames_to_bytes: index = r * 42 + g * 6 + b
+
+
+def cube_palette() -> list:
+    """The 252 RGB triples of the cube, flat, padded to 768 entries (PIL ``putpalette``)."""
+    lr, lg, lb = CUBE_LEVELS
+    pal = [int(round(v)) for r in range(lr) for g in range(lg) for b in range(lb)
+           for v in (r * 255 / (lr - 1), g * 255 / (lg - 1), b * 255 / (lb - 1))]
+    return pal + [0] * (768 - len(pal))
+
+
+def frames_to_bytes(frames: torch.Tensor, *, rgb: bool = True, palette: bool = False, dither: bool = True):
+    """One decoded video ``[3, F, H, W]`` in [-1, 1] (fp32 / fp16, CUDA; the pixel plane contiguous) -> ``(rgb uint8
+    [F, H, W, 3] or None, idx uint8 [F, H, W] or None)``: the reference's ``((x + 1) / 2 * 255).clamp(0, 255).to(uint8)``
+    and / or indices into ``cube_palette()``."""
+    if not frames.is_cuda or frames.dim() != 4 or frames.shape[0] != 3 or frames.dtype not in (torch.float16, torch.float32):
+        raise NativeError("frames_to_bytes: frames must be a CUDA fp16 / fp32 tensor [3, F, H, W]")
+    _, F, H, W = frames.shape
+    if frames.stride(3) != 1 or frames.stride(2) != W:
+        frames = frames.contiguous()
+    out_rgb = torch.empty((F, H, W, 3), dtype=torch.uint8, device=frames.device) if rgb else None
+    out_idx = torch.empty((F, H, W), dtype=torch.uint8, device=frames.device) if palette else None
+    _check(load().svdpp_frames_to_bytes(frames.data_ptr(), 1 if frames.dtype == torch.float32 else 0, frames.stride(0),
+                                        frames.stride(1), F, H, W, out_rgb.data_ptr() if rgb else None,
+                                        out_idx.data_ptr() if palette else None, 1 if dither else 0, _stream()),
+           "svdpp_frames_to_bytes")
+    _count(1)
+    return out_rgb, out_idx
 
 
 def time_conv_out(out: torch.Tensor, x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, B: int, F: int, HW: int
