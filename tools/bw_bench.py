@@ -146,6 +146,19 @@ def run_cases(F_, filters=(), quiet=False):
         return mk, run, nb, nb
     cases.append(("im2col stride 2, 72x128 C=320", *im2col_case(), "reads x once (ideal), writes 9/4 x"))
 
+    def frames_case(palette, Fv=25, Hp=576, Wp=1024):
+        n = Fv * Hp * Wp
+
+        def mk():      # the permuted view decode_latents returns: [F, 3, H, W] storage seen as [3, F, H, W]
+            return (torch.rand(Fv, 3, Hp, Wp, device=DEV) * 2 - 1,)
+
+        def run(s):
+            native.frames_to_bytes(s[0].permute(1, 0, 2, 3), rgb=not palette, palette=palette)
+        nb = n * 12 + n * (1 if palette else 3)
+        return mk, run, nb, nb
+    cases.append(("frames_to_bytes 25f 576x1024 fp32 -> RGB bytes", *frames_case(False), "output side of the image -> video run"))
+    cases.append(("frames_to_bytes 25f 576x1024 fp32 -> palette indices", *frames_case(True), "fixed 6x7x6 cube, ordered dither"))
+
     out_path = os.path.join(ROOT, "gpurun_out", "bw_bench.jsonl")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     records = []
