@@ -66,8 +66,8 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-library-baseline", action="store_true")
     p.add_argument("--cpu-sample-frames", type=int, default=6,
-                   help="frames of the CPU baseline's bounded sample (6 of 25 = 10-20 s of CPU work per step on the box's "
-                        "16 cores; 2 frames took 3.9 s and, being cache-friendlier, flattered the CPU by 25 %%)")
+                   help="frames of the CPU baseline's bounded sample: 6 of 25 = 12.3 s of CPU work per step on the box's 16 "
+                        "cores (2 frames: 3.9 s, a 4 %% better CPU number per frame)")
     p.add_argument("--schedule", default="ring", choices=["ring", "linear"],
                    help="N>1: 'ring' rotates the stage->rank placement per video (no fill/drain bubble, no stage "
                         "imbalance); 'linear' is the reference's fixed placement (stage s on rank s)")
