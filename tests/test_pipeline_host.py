@@ -180,6 +180,57 @@ def _single_process(total_steps, n_samples=3):
     return out
 
 
+VERIFY_CASES = ("same", "shape", "dtype", "split")
+
+
+def _verify_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    torch.set_num_threads(1)
+    init_distributed(backend="gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    for case in VERIFY_CASES:
+        spec = _spec()
+        total, uneven = 28, False
+        if case == "shape" and rank == 1:
+            spec = LatentSpec(shape=torch.Size(list(spec.shape[:-1]) + [spec.shape[-1] + 1]), dtype=spec.dtype, device=spec.device)
+        if case == "dtype" and rank == 1:
+            spec = LatentSpec(shape=spec.shape, dtype=torch.float64, device=spec.device)
+        if case == "split":            # rank 0 splits 25 steps unevenly (13 + 12), rank 1 believes in 24 (12 + 12)
+            total, uneven = (25, True) if rank == 0 else (24, False)
+        stage = PipelineStage(_model(), PipelineConfig(total, world, rank, list(range(total)), spec, allow_uneven=uneven))
+        try:
+            stage.verify_peers()
+            q.put((case, rank, "ok"))
+        except RuntimeError as e:
+            q.put((case, rank, str(e)))
+    dist.barrier()
+    finalize_distributed()
+
+
+@pytest.mark.timeout(300)
+def test_verify_peers_names_the_disagreement_on_every_rank():
+    """SURVEY section 5 (failure detection): stages that disagree on the latent or on the split raise at once, on every rank,
+    instead of hanging in recv until the process-group timeout as the reference does."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_verify_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2 * len(VERIFY_CASES)):
+        case, rank, msg = q.get(timeout=180)
+        got[(case, rank)] = msg
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[("same", 0)] == got[("same", 1)] == "ok"
+    for case in VERIFY_CASES[1:]:
+        a, b = got[(case, 0)], got[(case, 1)]
+        assert a == b and a.startswith("pipeline stages disagree: ") and "rank 1" in a, (case, a, b)
+    # one process: nothing to compare
+    PipelineStage(_model(), PipelineConfig(4, 1, 0, [3, 2, 1, 0], _spec())).verify_peers()
+
+
 def _negotiate_worker(rank, world, port, total_steps, n_samples, q):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     torch.set_num_threads(1)

@@ -255,6 +255,7 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
     cfg = PipelineConfig(total_steps=args.total_steps, world_size=world, rank=rank,
                          timesteps=list(range(args.total_steps)), latent_spec=spec, allow_uneven=args.allow_uneven)
     stage = PipelineStage(model=model, config=cfg, transport=args.transport or ("peer" if distributed else "nccl"))
+    stage.verify_peers()       # every rank agrees on the latent and on the split, or all of them raise now
     rec["transport_note"] = stage.negotiate_transport()
     rec["transport"] = stage.transport if distributed else None
     LOGGER.info("Rank %d: steps %d to %d; generating %d samples (guidance_scale=%s)", rank, stage.step_range.start,

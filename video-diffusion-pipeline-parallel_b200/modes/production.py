@@ -94,6 +94,7 @@ def main(argv=None):
     cfg = PipelineConfig(total_steps=args.total_steps, world_size=world, rank=rank, timesteps=timesteps,
                          latent_spec=spec, allow_uneven=args.allow_uneven)
     stage = PipelineStage(model=model, config=cfg)
+    stage.verify_peers()       # ranks that disagree on the latent or the split raise now instead of hanging in recv
     t0 = time.perf_counter()
     if args.schedule == "ring" and world > 1:
         done = stage.run_many_ring(args.num_samples, input_supplier=supplier)

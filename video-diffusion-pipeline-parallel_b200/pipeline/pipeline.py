@@ -165,6 +165,40 @@ class PipelineStage:
             self._peer = PeerHandoff(spec.shape, spec.dtype, spec.device)
         return self._peer
 
+    def verify_peers(self) -> None:
+        """Collective sanity check before the first handoff (failure detection): every rank publishes its
+        latent shape / dtype, ``total_steps`` and step range; a mismatch raises on EVERY rank with the offending ranks named.
+        The reference has no such check - ranks that disagree on the ``LatentSpec`` they agreed on "out of band"
+        (pipeline.py:25-34) simply hang in ``recv`` until the 10-minute process-group timeout.  Optional, one tiny
+        ``all_gather``; not called by ``run`` / ``run_many`` so that message order stays the reference's."""
+        cfg = self.config
+        if cfg.world_size <= 1:
+            return
+        shape = list(cfg.latent_spec.shape)
+        if len(shape) > 8:
+            raise ValueError("verify_peers supports latents of up to 8 dimensions")
+        dtypes = [torch.float16, torch.float32, torch.bfloat16, torch.float64]
+        code = dtypes.index(cfg.latent_spec.dtype) if cfg.latent_spec.dtype in dtypes else -1
+        mine = torch.tensor([len(shape)] + shape + [0] * (8 - len(shape)) +
+                            [code, cfg.total_steps, cfg.world_size, self.step_range.start, self.step_range.end],
+                            dtype=torch.int64, device=cfg.latent_spec.device)
+        everyone = [torch.empty_like(mine) for _ in range(cfg.world_size)]
+        dist.all_gather(everyone, mine)
+        rows = [t.tolist() for t in everyone]
+        problems = []
+        for r, row in enumerate(rows):
+            if row[:12] != rows[0][:12]:
+                problems.append(f"rank {r} has latent/steps/world {row[:12]} but rank 0 has {rows[0][:12]}")
+        expect = 0
+        for r, row in enumerate(rows):
+            if row[12] != expect or row[13] < row[12]:
+                problems.append(f"rank {r} owns steps [{row[12]}, {row[13]}) but the slices up to it end at {expect}")
+            expect = row[13]
+        if expect != rows[0][10]:
+            problems.append(f"the step slices end at {expect}, not at total_steps = {rows[0][10]}")
+        if problems:
+            raise RuntimeError("pipeline stages disagree: " + "; ".join(problems))
+
     def negotiate_transport(self) -> Optional[str]:
         """Collective: set up the peer-mapped slots now and, if the symmetric-memory rendezvous fails on ANY rank, put
         every rank on NCCL send / recv instead.  Returns a note when it fell back, else None.  Optional - without it the
