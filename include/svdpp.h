@@ -110,6 +110,7 @@ typedef struct svdpp_gemm_desc {
  *   2 = CTA pair (cta_group::2), 256x160   3 = CTA pair, 256x256 (GEGLU rows interleaved [128 value | 128 gate])
  *   6 = CTA pair, 256x320 as two N=160 MMAs per k-step, halves rotating through three TMEM buffers (no GEGLU)
  *   5 = impl 3 with 8 instead of 16 GEGLU epilogue warps (A/B measurements)
+ *   7 = CTA pair, 256x128 (no GEGLU): impl 4's width, half the B-operand traffic per SM
  *   1 = plain CUDA-core kernel (slow; bring-up cross-check) */
 int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream stream);
 

@@ -55,7 +55,7 @@ def _with_guard(res: dict, g: "_Guarded") -> dict:
 
 
 def _bn(impl):
-    return {3: 256, 5: 256, 4: 128, 6: 320}.get(impl, native.GEMM_BN)
+    return {3: 256, 5: 256, 4: 128, 7: 128, 6: 320}.get(impl, native.GEMM_BN)
 
 
 def _pad_n(w, mult=native.GEMM_BN):
@@ -711,6 +711,15 @@ ALL_CHECKS = {
     "bn128_gemm_split": lambda: gemm_linear(M=700, N=512, impl=4, K=384, split=True),
     "bn128_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=128, impl=4),
     "bn128_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=128, impl=4),
+    "pair128_gemm_plain": lambda: gemm_linear(M=256, N=128, K=64, impl=7, epilogue="bias"),
+    "pair128_gemm_linear": lambda: gemm_linear(M=300, N=1280, K=320, impl=7),
+    "pair128_gemm_big": lambda: gemm_linear(M=3600, N=1280, K=1280, impl=7),
+    "pair128_gemm_mtail_odd": lambda: gemm_linear(M=385, N=256, K=128, impl=7),
+    "pair128_gemm_many_tiles": lambda: gemm_linear(M=70000, N=128, K=384, impl=7),
+    "pair128_gemm_split": lambda: gemm_linear(M=700, N=512, impl=7, K=384, split=True),
+    "pair128_conv3x3_w16": lambda: conv3x3(B=1, Fr=3, H=9, W=16, C=64, Cout=128, impl=7),
+    "pair128_conv3x3_w64": lambda: conv3x3(B=1, Fr=2, H=24, W=64, C=128, Cout=128, impl=7),
+    "pair128_conv_temporal": lambda: conv_temporal(B=2, Fr=5, H=4, W=32, C=128, impl=7),
     "pair256_gemm_nstore_partial": lambda: gemm_linear(M=700, N=960, K=320, impl=3, epilogue="full"),
     "pair256_gemm_nstore_partial_bias": lambda: gemm_linear(M=300, N=1920, K=640, impl=3, epilogue="bias"),
     "pair320_gemm_plain": lambda: gemm_linear(M=512, N=320, K=64, impl=6, epilogue="bias"),

@@ -1227,7 +1227,9 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
   //         148 SMs' last wave better than 128x160 or 256x256
   // impl 5: impl 3 with 8 instead of 16 GEGLU epilogue warps (A/B measurements only)
   // impl 6: CTA pairs with 256x320 tiles, one accumulator stage (N a multiple of 320, no GEGLU)
-  const int BN = (impl == 3 || impl == 5) ? 256 : (impl == 4 ? 128 : (impl == 6 ? 320 : 160));
+  // impl 7: CTA pairs with 256x128 tiles (N a multiple of 128, no GEGLU): impl 4's width with half the B traffic per SM -
+  //         for the N = 128 layers at very large M (the VAE decoder's full-resolution convolutions)
+  const int BN = (impl == 3 || impl == 5) ? 256 : ((impl == 4 || impl == 7) ? 128 : (impl == 6 ? 320 : 160));
   SVDPP_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
   SVDPP_CHECK_ARG(d->K % 64 == 0, "gemm: K=%d must be a multiple of 64", d->K);
   SVDPP_CHECK_ARG(d->N % BN == 0, "gemm: N=%d must be a multiple of %d (pad the weight)", d->N, BN);
@@ -1325,10 +1327,11 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(sp);
     return check_launch("gemm_simt_kernel");
   }
-  SVDPP_CHECK_ARG(impl == 0 || (impl >= 2 && impl <= 6), "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(impl == 0 || (impl >= 2 && impl <= 7), "gemm: unknown impl %d", impl);
+  SVDPP_CHECK_ARG(!(impl == 7 && d->geglu), "gemm: impl 7 has no GEGLU epilogue");
   SVDPP_CHECK_ARG(!(impl == 6 && d->geglu), "gemm: impl 6 has no GEGLU epilogue");
   SVDPP_CHECK_ARG(!(impl == 4 && d->geglu), "gemm: impl 4 has no GEGLU epilogue");
-  const bool two = impl == 2 || impl == 3 || impl == 5 || impl == 6;  // CTA pairs (cta_group::2)
+  const bool two = impl == 2 || impl == 3 || impl == 5 || impl == 6 || impl == 7;  // CTA pairs (cta_group::2)
 
   CUtensorMap tmA, tmA2, tmB;
   if (!d->conv) {
@@ -1381,6 +1384,7 @@ extern "C" int svdpp_gemm_f16(const svdpp_gemm_desc* d, int impl, svdpp_stream s
     if (encode_tmap_f16(&tmB, d->Wt, 2, dims, str, box)) return -5;
   }
   if (impl == 4) return launch_tc<128, false, false>(tmA, tmA2, tmB, p, stream);
+  if (impl == 7) return launch_tc<128, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 6) return launch_tc<320, false, true>(tmA, tmA2, tmB, p, stream);
   if (impl == 5 && d->geglu) return launch_tc<256, true, true, 8>(tmA, tmA2, tmB, p, stream);
   if (impl == 5) return launch_tc<256, false, true>(tmA, tmA2, tmB, p, stream);

@@ -16,6 +16,7 @@ last blocks; these kernels accumulate in fp32 and only store fp16 between layers
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Mapping, Optional, Tuple
 
@@ -102,7 +103,8 @@ class NativeVAE(nn.Module):
     def _pack(self, w2d: torch.Tensor, b: Optional[torch.Tensor]) -> _Lin:
         n = w2d.shape[0]
         t = self._tile(n)
-        impl = 3 if t == 256 else 4
+        # N = 128 layers: one CTA per 128x128 tile (impl 4), or CTA pairs on 256x128 tiles (impl 7, SVDPP_VAE_PAIR128=1)
+        impl = 3 if t == 256 else (7 if os.environ.get("SVDPP_VAE_PAIR128", "0") not in ("", "0") else 4)
         return _Lin(self._keep(_pad_cols(_pad_rows(w2d, t))), self._keep(_pad_rows(b, t)) if b is not None else None, n,
                     impl=impl)
 
