@@ -24,7 +24,7 @@ a = ap.parse_args()
 if a.conv:
     B_, F_, H_, W_, C_ = a.conv
     a.M, a.K = B_ * F_ * H_ * W_, (3 if a.temporal else 9) * C_
-bn = {3: 256, 5: 256, 4: 128, 6: 320}.get(a.impl, 160)
+bn = {3: 256, 5: 256, 4: 128, 7: 128, 6: 320}.get(a.impl, 160)
 npad = (a.N + bn - 1) // bn * bn
 w = torch.zeros(npad, a.K, device="cuda", dtype=torch.float16)
 w[:a.N] = torch.randn(a.N, a.K, device="cuda").half() * a.K ** -0.5
