@@ -48,6 +48,8 @@ struct Tuning {
   int tma_r1;     // GEMM residual tile through TMA tensor loads (with tma_store)
   int epi_dma;    // GEMM: DMA-lane epilogue with two staging tiles for short main loops
   int epi_dma_max_kb;  // ... for K / 64 <= this
+  int two_prod;        // GEMM: a second TMA producer warp (warp 3) takes every other k-block when K / 64 >= two_prod_min_kb
+  int two_prod_min_kb;
   int splitk;          // GEMM impl 6: split-K tail when the descriptor carries a workspace
   int splitk_min_kb;   // ... fewest k-blocks per slice
   int r1_prefetch_max_kb;   // GEMM: producer warp prefetches the residual tile into L2 for K / 64 <= this (0: never)

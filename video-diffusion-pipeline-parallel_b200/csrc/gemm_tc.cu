@@ -57,6 +57,10 @@ struct GemmParams {
   // residual loads, and two staging tiles alternate - the second one lives in the last pipeline stages, which a
   // short main loop does not need.  The epilogue warps never wait for a store to drain or a residual to arrive.
   int epi_dma;
+  // 1: warp 3 is a second TMA producer taking every other k-block (never together with epi_dma, whose lane it is).
+  // tools/ubench/fill.cu: one issuing thread sustains one k-block per ~500-590 clocks whatever its size, two producers
+  // 300-440 - more than the 256 / 320 / 512 clocks of MMAs a 128 / 160 / 256-wide tile spends on a k-block.
+  int two_prod;
   // Split-K tail (256x320 pair tiles only).  The tiles of the last, partial wave (sk_r of them, after sk_full tiles
   // in full waves) are each computed by `splitk` CTA pairs over disjoint K ranges; the fp32 partial accumulators meet
   // in the workspace sk_ws, and once a tile's partials are all there (counter in sk_cnt) every participating CTA
@@ -269,14 +273,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  // ------------------------------------------------------------------ TMA producer (warp 0; with p.two_prod also warp 3)
+  auto produce = [&](const int me, const int nprod) {
     // Lane 0 owns the ring (waits, expect_tx, the B tile); in conv mode lane r < nrows issues the
     // window box of image row r, whose coordinates are computed once per tile.  Keep this loop lean: the
     // warp issues one k-block every ~320 cycles at peak.  (Tried and removed: an L2 prefetch stream 16 k-blocks
     // ahead via cp.async.bulk.prefetch.tensor lowered throughput by ~40 % on B200.)
     int stage = 0;
     uint32_t phase = 0;
+    int kcount = 0;  // k-blocks of this CTA so far: with two producers, warp `me` fills those with kcount % 2 == me
     for (int item = 0; item < n_items; ++item) {
       const bool is_tail = item >= n_full_items;
       const int w = is_tail ? tail_w : work_first + item * work_stride;
@@ -293,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cf = img % p.cF;
         cb = img / p.cF;
       }
-      if (!GEGLU && p.prefetch_r1) {
+      if (!GEGLU && p.prefetch_r1 && me == 0) {
         // the epilogue of this tile will read R1[m0 .. m0+127][n0 .. n0+BN) a whole main loop from now: start the
         // HBM -> L2 fetch here so that its loads find the lines in L2 (K = 320 layers are epilogue-latency bound)
         const int n_first = (w % p.n_tiles) * BN;
@@ -312,7 +317,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        if (lane == 0) {
+        const bool mine = nprod == 1 || (kcount & 1) == me;
+        ++kcount;
+        if (lane == 0 && mine) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           if constexpr (TWO) {
             if (cta_rank == 0)
@@ -346,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (p.conv) {
-          if (lane < p.nrows) {
+          if (lane < p.nrows && mine) {
             if constexpr (TWO)
               tma2_load_5d(sa + lane * p.bw * 128, &tmA, &full[stage], kc * 64, cw * p.cstride + p.taps[tap][0],
                            ch * p.cstride + p.taps[tap][1], cf + p.taps[tap][2], cb);
@@ -365,6 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  };
+  if (warp == 0) {
+    produce(0, p.two_prod ? 2 : 1);
+  } else if (warp == 3 && p.two_prod) {
+    produce(1, 2);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // The WHOLE warp runs the loop and one elected lane executes the tcgen05 instructions.  Under `if (lane == 0)`
@@ -1175,6 +1187,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     if (dma_ok && (tuning().epi_dma >= 2 || (tuning().epi_dma == 1 && Cfg::STEAL == 1 && p.num_kb <= tuning().epi_dma_max_kb)))
       p.epi_dma = 1;
   }
+  p.two_prod = (tuning().two_prod && !p.epi_dma && p.num_kb >= tuning().two_prod_min_kb) ? 1 : 0;
   if constexpr (TWO) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     int clusters = num_sms() / 2;
