@@ -39,6 +39,10 @@ int svdpp_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   "tma_r1"     1 (with tma_store): the residual tile R1 reaches the epilogue through TMA tensor loads; 0: per-thread loads
  *   "epi_dma"    1: GEMMs with 256/128-wide tiles and K <= 64 * "epi_dma_max_kb" (default 5) run their epilogue I/O on a
  *                   dedicated DMA lane with two staging tiles; 2: wherever possible; 0: never (SVDPP_EPI_DMA, SVDPP_EPI_DMA_MAX_KB)
+ *   "two_prod"   1 (default): GEMMs with K >= 64 * "two_prod_min_kb" (default 6) that do not use the DMA lane fill their smem
+ *                   ring from TWO producer warps taking alternate k-blocks (one issuing thread sustains a k-block per
+ *                   ~500-590 clocks whatever its size - tools/ubench/fill.cu - which capped the 128 / 160 / 256-wide
+ *                   tiles); 0: one producer warp (SVDPP_TWO_PROD)
  *   "splitk"     1: impl 6 splits the tiles of a short last wave along K when the descriptor carries splitk_ws; 0: never
  *                   ("splitk_min_kb": fewest 64-wide k-blocks a slice may get, default 4; "splitk_min_total_kb": only for
  *                   K / 64 >= this, default 64)

@@ -4,7 +4,8 @@
 //   warp 0      TMA producer   global -> 128B-swizzled smem ring (A tile 128x64, B tile BNx64)
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages)
-//   warp 3      epilogue DMA lane (p.epi_dma): issues the output tensor stores and residual tensor loads
+//   warp 3      epilogue DMA lane (p.epi_dma): issues the output tensor stores and residual tensor loads; otherwise
+//               (p.two_prod, long main loops) a SECOND TMA producer taking every other k-block
 //   warps 4..11 epilogue       tcgen05.ld accumulator rows -> bias/rowvec/residual/GEGLU -> fp16 into a staging tile in
 //               smem; two warps per TMEM lane quarter, each taking every other column chunk.  The staging tile is
 //               kept in the 64-byte swizzle of a tensor map over the output and leaves through TMA tensor stores
@@ -276,8 +277,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ------------------------------------------------------------------ TMA producer (warp 0; with p.two_prod also warp 3)
   auto produce = [&](const int me, const int nprod) {
     // Lane 0 owns the ring (waits, expect_tx, the B tile); in conv mode lane r < nrows issues the
-    // window box of image row r, whose coordinates are computed once per tile.  Keep this loop lean: the
-    // warp issues one k-block every ~320 cycles at peak.  (Tried and removed: an L2 prefetch stream 16 k-blocks
+    // window box of image row r, whose coordinates are computed once per tile.  Keep this loop lean: ONE issuing
+    // thread gets through a k-block (barrier wait, expect_tx, the TMA instructions) in 500-590 clocks however small the
+    // boxes are (tools/ubench/fill.cu), which is more than the MMAs of a 128 / 160 / 256-wide tile take - hence the
+    // second producer warp for long main loops.  (Tried and removed: an L2 prefetch stream 16 k-blocks
     // ahead via cp.async.bulk.prefetch.tensor lowered throughput by ~40 % on B200.)
     int stage = 0;
     uint32_t phase = 0;
