@@ -130,7 +130,8 @@ __device__ __forceinline__ long long out_row(const GemmParams& p, int m) {
 // TWO: CTA pairs (cta_group::2).  The pair computes a 256 x BN tile: each CTA loads its own 128 rows of A
 // and HALF of the B tile, the leader issues M = 256 MMAs that read B from both CTAs' smem, and each CTA
 // keeps the accumulator of its own 128 rows in its own TMEM.  Per SM and k-block this moves 26 KB instead of
-// 36 KB from L2 (the L2 -> SM path, not the tensor pipe, caps the one-CTA kernel near 1 PFLOP/s).
+// 36 KB from L2 (read in round 1 as an L2 -> SM cap of the one-CTA kernel near 1 PFLOP/s; tools/ubench/fill.cu later showed
+// the cap was the single producer thread's k-block rate - see two_prod).
 template <int BN, bool GEGLU, bool TWO, int EW_ = 0>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
@@ -147,7 +148,7 @@ struct GemmCfg {
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
   // BN = 320 (CTA pairs only): the whole N = 320 of the level-0 layers in one 256 x 320 pair tile, issued as two
   // N = 160 MMAs per k-step.  Per CTA and k-block 36 KB come from L2 for 5.2 MFLOP (145 FLOP/B against 71 for the
-  // one-CTA 128x160 tile): the ~6300 B/clk L2->SM cap is what holds the narrow tiles near 0.9 PFLOP/s.  320 fp32
+  // one-CTA 128x160 tile): the narrow tiles sat near 0.9 PFLOP/s (producer-issue-bound, see two_prod; the L2->SM path delivers 10.8 KB/clk).  320 fp32
   // columns leave room for ONE accumulator stage in the 512 TMEM columns, so TMEM reads of the epilogue are not
   // overlapped with the next main loop (stores still are); worth it for K >= 1280.
   static constexpr int NACC = BN > 256 ? 1 : 2;
