@@ -201,8 +201,11 @@ def generate(args, *, image_encoder=None, vae=None, model=None, feature_extracto
         from ..distributed.backend import resolve_backend
         from ..distributed.setup import init_distributed
         init_distributed(backend=resolve_backend(None, simulator=False), rank=rank, world_size=world)
-    model_id = args.model_id if (os.path.isdir(args.model_id) or args.model_id.startswith("random-init")) else "random-init"
-    if model_id != args.model_id:
+    model_id = args.model_id
+    if model_id == HUB_ID and not os.path.isdir(model_id):
+        # the reference's default is the hub id; there is no network here.  Any OTHER path that does not exist is an error
+        # (the loaders raise FileNotFoundError) rather than a silent switch to noise weights.
+        model_id = "random-init"
         LOGGER.warning("'%s' is not a local directory (no network here): using seeded random-init weights", args.model_id)
 
     t0 = _sync_time(device)
