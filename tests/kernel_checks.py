@@ -860,6 +860,9 @@ for _n in ("tc_gemm_linear", "tc_gemm_big", "tc_gemm_split", "pair_gemm_big", "p
            "pair256_gemm_nstore_partial", "pair320_gemm_linear", "pair320_gemm_big", "bn128_gemm_big",
            "pair256_gemm_mtail_odd", "pair320_gemm_mtail_odd"):
     ALL_CHECKS["r1ldg_" + _n] = _tuned(ALL_CHECKS[_n], tma_r1=0)       # residual tile through per-thread loads (TMA loads are the default)
+for _n in ("tc_gemm_big", "pair_gemm_big", "pair256_gemm_big", "pair320_gemm_big", "bn128_gemm_big", "pair128_gemm_big",
+           "pair320_conv3x3_w32", "pair256_conv_temporal", "tc_conv3x3_w32"):
+    ALL_CHECKS["oneprod_" + _n] = _tuned(ALL_CHECKS[_n], two_prod=0)    # one TMA producer warp (two are the default for K >= 384)
 ALL_CHECKS["tc_gemm_many_tiles"] = lambda: gemm_linear(M=40000, N=640, K=320, impl=0)          # ~8 tiles per CTA
 ALL_CHECKS["pair256_gemm_many_tiles"] = lambda: gemm_linear(M=40000, N=1024, K=320, impl=3)
 ALL_CHECKS["pair320_gemm_many_tiles"] = lambda: gemm_linear(M=70000, N=640, K=320, impl=6)
