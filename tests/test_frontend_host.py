@@ -172,3 +172,26 @@ def test_local_snapshot_reader(tmp_path):
         (tmp_path / "empty" / "vae").mkdir(parents=True)
         fw.load_component(str(tmp_path / "empty"), "vae", device="cpu")
     assert fw.is_random_init("random-init:7") and fw.random_init_seed("random-init:7") == 7 and fw.random_init_seed("random-init") == 0
+
+
+def test_colour_cube_palette_and_index_restatement():
+    """The fixed palette of svdpp_frames_to_bytes and the numpy restatement of its quantiser (the oracle of the
+    frames_to_bytes_* GPU checks): 252 distinct colours, rounding to the nearest level without dither (error at most half a
+    cube step), within one step with the ordered dither, and a dither that is unbiased over a 4 x 4 cell."""
+    import kernel_checks as kh          # importable without a GPU: only its check functions touch the device
+    from vdpp_b200 import native
+    pal = np.array(native.cube_palette(), dtype=np.int32).reshape(256, 3)
+    assert len({tuple(c) for c in pal[:252]}) == 252 and (pal[252:] == 0).all()
+    assert tuple(pal[0]) == (0, 0, 0) and tuple(pal[251]) == (255, 255, 255) and tuple(pal[1 * 42 + 2 * 6 + 3]) == (51, 85, 153)
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, size=(2, 8, 12, 3), dtype=np.uint8)
+    rgb[0, 0, :4] = [[0, 0, 0], [255, 255, 255], [25, 21, 26], [26, 22, 25]]
+    plain = kh.cube_index_reference(rgb, dither=False)
+    err = np.abs(pal[plain] - rgb.astype(np.int32))
+    assert err[..., 0].max() <= 26 and err[..., 1].max() <= 22 and err[..., 2].max() <= 26
+    dith = kh.cube_index_reference(rgb, dither=True)
+    errd = np.abs(pal[dith] - rgb.astype(np.int32))
+    assert errd[..., 0].max() <= 51 and errd[..., 1].max() <= 43 and errd[..., 2].max() <= 51 and int(dith.max()) < 252
+    flat = np.full((1, 4, 4, 3), 100, dtype=np.uint8)                # a flat grey: the 16 dither thresholds average it out
+    mean = pal[kh.cube_index_reference(flat, dither=True)].reshape(-1, 3).mean(axis=0)
+    assert np.abs(mean - 100).max() <= 4
